@@ -1,0 +1,107 @@
+"""TEST INFRASTRUCTURE ONLY -- vectorised NumPy float64 restatement of the
+reference's ``drones.step()`` path over E environments.
+
+Second, independent restatement (the first is ``drone_oracle.c``); the two are
+cross-checked against each other and against the golden vectors recorded from
+the unmodified reference (``tests/test_oracle_golden.py``).  Parity status:
+PINNED by ``tests/golden/``.  Never imported by the product package.
+
+Reference citations (file:line in /root/reference/drone_env.py):
+  integrate 227-238 | distance_data 295-334 | rewards 260-293 |
+  localized_states 336-401 | termination 248-256
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SENTINEL = 9.99e3        # drone_env.py:330-332
+ZERO_EPS = -10 ** -6     # drone_env.py:320
+GHOST_FACTOR = 1.1       # drone_env.py:386
+GOAL_TOL = 0.2           # drone_env.py:251
+
+
+def _norm_blas(x, y):
+    """sqrt(ddot(v, v)) as OpenBLAS evaluates it for 2-vectors: fma(y, y, x*x).
+
+    NumPy has no fma ufunc; emulate it exactly with a Dekker/Veltkamp split
+    (error-free product) so the restatement is bit-identical to the C oracle.
+    """
+    xx = x * x
+    # two-product y*y = p + e exactly
+    p = y * y
+    c = 134217729.0 * y  # 2**27 + 1
+    hi = c - (c - y)
+    lo = y - hi
+    e = ((hi * hi - p) + 2.0 * hi * lo) + lo * lo
+    # fma(y,y,xx) = round(p + e + xx): two-sum of p and xx, then add the errors
+    s = p + xx
+    bb = s - p
+    err = (p - (s - bb)) + (xx - bb)
+    return np.sqrt(s + (err + e))
+
+
+def observe(pos, vel, radius, xF, d_safety, deltas, k, simplify, collision_weight, dt=0.05):
+    """rewards() (drone_env.py:260-293) for pos[E,n,2]; returns dict of arrays."""
+    E, n, _ = pos.shape
+    q, b = 2 * dt, collision_weight * dt
+    dx = pos[:, :, None, 0] - pos[:, None, :, 0]
+    dy = pos[:, :, None, 1] - pos[:, None, :, 1]
+    with np.errstate(all="ignore"):
+        raw = _norm_blas(dx, dy) - radius[None, :, None] - radius[None, None, :]
+        ds = np.broadcast_to(d_safety[None, :, None], raw.shape)
+        d = np.where(ds < raw, ds, raw)                       # python min(raw, ds), :318
+        d = np.where(d == 0, ZERO_EPS, d)                     # :319-320
+        dn = ds / d                                           # :321
+        eye = np.eye(n, dtype=bool)[None]
+        self_d = np.where(d_safety < -2 * radius, d_safety, -radius - radius)  # :323
+        d = np.where(eye, self_d[None, :, None], d)
+        dn = np.where(eye, 1.0, dn)                           # :325
+        coll = dn <= 0                                        # :327
+        nd = d <= deltas[None, None, :]                       # :328 (column broadcast)
+        logd = np.where(coll, SENTINEL, np.log(np.where(coll, SENTINEL, dn)))  # :330-332
+        g = xF[None] - pos
+        nrm = np.sqrt(g[..., 0] * g[..., 0] + g[..., 1] * g[..., 1])
+        goal = q * (nrm * nrm)                                # :276
+        r = -np.nan_to_num(goal + b * np.sum(logd * nd, 2))   # :282,287
+        true_r = -np.nan_to_num(goal + b * np.sum(logd, 2))   # :283,288
+        ncoll = coll.sum((1, 2)).astype(np.int32)             # :284
+        order = np.argsort(d, axis=2, kind="stable")          # :338, ties -> lowest index
+        in_range = nd.sum(2) - 1                              # :346
+        cols = 2 if simplify else 5
+        z = np.zeros((E, n, k + 1, cols))
+        Ni = np.full((E, n, k + 1), -1, np.int32)
+        zi = -(xF[None] - pos)                                # :357
+        z[:, :, 0, 0:2] = zi
+        if not simplify:
+            z[:, :, 0, 2:4] = vel
+            z[:, :, 0, 4] = radius[None]
+        Ni[:, :, 0] = np.arange(n)[None]
+        zn = _norm_blas(zi[..., 0], zi[..., 1])
+        ghost = zi / zn[..., None] * deltas[None, :, None] * GHOST_FACTOR  # :386
+        ee = np.arange(E)[:, None]
+        for kth in range(1, k + 1):
+            j = order[:, :, kth]
+            inside = kth <= in_range                          # :362
+            rel = pos[ee, j] - pos                            # :368
+            z[:, :, kth, 0:2] = np.where(inside[..., None], rel, ghost)
+            if not simplify:
+                z[:, :, kth, 2:4] = vel[ee, j]
+                z[:, :, kth, 4] = radius[j]
+            Ni[:, :, kth] = np.where(inside, j, -1)
+        # reference appends neighbours contiguously; "inside" is a prefix so -1s trail
+        dsort = np.take_along_axis(d, order[:, :, : min(n, k + 2)], 2)
+        tie = (dsort[:, :, 1:] == dsort[:, :, :-1]).any(2)
+    return dict(r=r, true_r=true_r, z=z, Ni=Ni, ncoll=ncoll, tie=tie, d=d)
+
+
+def step(pos, vel, t, act, radius, xF, d_safety, deltas, k, simplify, collision_weight,
+         dt=0.05, max_time_steps=200):
+    """drones.step() (drone_env.py:214-258) for E envs; pos/vel/t updated in place."""
+    pos += dt * act          # A = I, B = dt*I (:78-79,235); rounding: x + round(dt*u)
+    vel[...] = act           # :238
+    out = observe(pos, vel, radius, xF, d_safety, deltas, k, simplify, collision_weight, dt)
+    g = xF[None] - pos
+    err = np.sqrt(g[..., 0] * g[..., 0] + g[..., 1] * g[..., 1])
+    out["finished"] = ((err <= GOAL_TOL).all(1) | (t >= max_time_steps - 1)).astype(np.uint8)  # :251
+    t += 1                   # :256
+    return out

@@ -1,0 +1,109 @@
+"""CPU: pin the oracles (C and NumPy restatements) to the golden vectors that
+oracle/make_golden.py recorded from the unmodified reference drone_env.py."""
+import numpy as np
+import pytest
+
+from helpers import FP64_TOL, assert_close, compare_obs, golden_names, load_golden
+from oracle import c_oracle, np_oracle
+
+
+def _c_env(g, E=1):
+    p = c_oracle.default_params(g["collision_weight"], g["dt"], g["max_time_steps"])
+    return c_oracle.OracleEnv(E, g["n"], g["end_points"], g["d_safety"], g["deltas"], g["radius"],
+                              g["k"], bool(g["simplify"]), p)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_c_oracle_teacher_forced(name):
+    """Every recorded step, fed the reference's own input state (batched as E=T envs)."""
+    g = load_golden(name)
+    T = len(g["ncoll"])
+    env = _c_env(g, E=T)
+    env.set_state(g["state_in"][:, :, 0:2], g["state_in"][:, :, 2:4], g["t_in"])
+    out = env.step(g["actions"])
+    assert_close(out.pos, g["state"][:, :, 0:2], 0.0, "pos (bit-exact)")
+    assert_close(out.vel, g["state"][:, :, 2:4], 0.0, "vel (bit-exact)")
+    assert_close(out.r, g["r"], FP64_TOL, "reward")
+    assert_close(out.true_r, g["true_r"], FP64_TOL, "true reward")
+    assert np.array_equal(out.ncoll.astype(np.int64), g["ncoll"]), "collision counts"
+    assert np.array_equal(out.finished, g["finished"]), "finished"
+    assert np.array_equal(out.t, g["t_in"] + 1)
+    assert np.array_equal(out.tie.astype(bool), g["tie"]), "tie mask"
+    compare_obs(out.z, out.Ni, g["z"], g["Ni"], g["tie"], FP64_TOL, name)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith(("free", "policy"))])
+def test_c_oracle_free_running(name):
+    """Whole episode from state0 with only the action stream shared."""
+    g = load_golden(name)
+    env = _c_env(g)
+    env.set_state(g["state0"][None, :, 0:2], g["state0"][None, :, 2:4], 0)
+    o0 = env.observe()
+    compare_obs(o0.z[0], o0.Ni[0], g["z0"], g["Ni0"], g["tie0"], FP64_TOL, name + " init")
+    ret = 0.0
+    for t in range(len(g["ncoll"])):
+        out = env.step(g["actions"][t][None])
+        assert_close(out.pos[0], g["state"][t][:, 0:2], 0.0, f"pos t={t}")
+        assert_close(out.r[0], g["r"][t], FP64_TOL, f"r t={t}")
+        assert int(out.ncoll[0]) == int(g["ncoll"][t])
+        assert int(out.finished[0]) == int(g["finished"][t])
+        ret += out.r[0].mean()
+    assert abs(ret - g["r"].mean(1).sum()) < 1e-9
+
+
+def test_c_oracle_rollout_matches_stepping():
+    g = load_golden("free_n10_g5_d1.0")
+    T = len(g["ncoll"])
+    env = _c_env(g)
+    env.set_state(g["state0"][None, :, 0:2], None, 0)
+    res = env.rollout(g["actions"][:, None])
+    assert_close(res["r"][:, 0], g["r"], FP64_TOL, "rollout r")
+    assert np.array_equal(res["ncoll"][:, 0].astype(np.int64), g["ncoll"])
+    assert np.array_equal(res["finished"][:, 0], g["finished"])
+    assert_close(res["agg"][0], [g["r"].mean(1).sum(), g["true_r"].mean(1).sum(), g["ncoll"].sum(), T],
+                 1e-9, "episode aggregates")
+
+
+def test_policy_episode_known_answer():
+    """seed 0, softmax8_n5 policy -> 200 steps, return -33.5050, 0 collisions."""
+    g = load_golden("policy_n5_seed0")
+    assert len(g["ncoll"]) == 200 and int(g["ncoll"].sum()) == 0
+    assert abs(g["r"].mean(1).sum() - (-33.5050)) < 5e-4
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_np_oracle_teacher_forced(name):
+    g = load_golden(name)
+    pos = g["state_in"][:, :, 0:2].copy(); vel = g["state_in"][:, :, 2:4].copy()
+    t = g["t_in"].copy()
+    out = np_oracle.step(pos, vel, t, g["actions"], g["radius"], g["end_points"].reshape(-1, 2),
+                         g["d_safety"], g["deltas"], g["k"], bool(g["simplify"]),
+                         g["collision_weight"], g["dt"], g["max_time_steps"])
+    assert_close(pos, g["state"][:, :, 0:2], 0.0, "pos (bit-exact)")
+    assert_close(out["r"], g["r"], FP64_TOL, "reward")
+    assert_close(out["true_r"], g["true_r"], FP64_TOL, "true reward")
+    assert np.array_equal(out["ncoll"].astype(np.int64), g["ncoll"])
+    assert np.array_equal(out["finished"], g["finished"])
+    compare_obs(out["z"], out["Ni"], g["z"], g["Ni"], g["tie"], FP64_TOL, name)
+
+
+def test_known_answer_facts():
+    """SURVEY section 4 edge cases, read back from the reference's own outputs."""
+    g = load_golden("edge_cases_n4")
+    # step 0: agents 0,1 are 0.15 apart -> both directions collide -> 2; +99.9 each
+    assert g["ncoll"][0] == 2
+    # step 1: exactly 0.2 apart -> d == 0 -> -1e-6 -> counts as a collision
+    assert g["ncoll"][1] == 2
+    # step 2: agent 2 exactly on its goal, fewer than k neighbours -> NaN ghost (0/0)
+    assert np.isnan(g["z"][2][2, 2, 0:2]).all()
+    # step 4: everyone within 0.2 of goal -> finished
+    assert g["finished"][4] == 1
+    # last two steps: t=198 not finished, t=199 finished by time
+    assert g["finished"][-2] == 0 and g["finished"][-1] == 1
+    env = _c_env(g, E=1)
+    env.set_state(g["state_in"][0][None, :, 0:2], None, 5)
+    out = env.step(g["actions"][0][None])
+    q, b = 2 * g["dt"], g["collision_weight"] * g["dt"]
+    assert abs(b * 9.99e3 - 99.9) < 1e-12
+    goal0 = q * np.sum((g["end_points"].reshape(-1, 2)[0] - out.pos[0, 0]) ** 2)
+    assert -out.r[0, 0] >= goal0 + 99.9 - 1e-9
