@@ -1,0 +1,212 @@
+/*
+ * dronestep.h -- C ABI of libdronestep.so, the B200 (sm_100a) implementation of
+ * the drone_env.step() hot path of AndreuMatoses/scalable-collision-avoidance-RL.
+ *
+ * The reference has no FFI of its own: the path sits behind the Python class
+ * `drone_env.drones` (reference drone_env.py:53).  Each entry point below names
+ * the reference code it replaces; the Python module `drone_env` of this
+ * repository binds them with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain C, POD structs, no C++ exceptions cross the boundary;
+ *   - every call returns an int status: DS_OK or a negative DS_ERR_*; the
+ *     message of the last failure on the calling thread is ds_last_error();
+ *   - device-pointer entry points (ds_step, ds_observe, ds_rollout,
+ *     ds_reduce_aggregates) only ENQUEUE work on the caller's cudaStream_t
+ *     (passed as void*), never synchronise and never allocate: every buffer is
+ *     caller-owned device memory;
+ *   - host-pointer entry points (*_host, ds_set_state, ds_get_state) copy
+ *     through staging buffers owned by the handle and synchronise the stream
+ *     before returning;
+ *   - a handle is bound to one device and one (n_envs, n_agents, k, precision);
+ *     it is not thread-safe; use one handle per rank;
+ *   - "Real" is float when ds_config.real_bytes == 4 and double when 8.  The
+ *     double instantiation is the parity path (reference arithmetic is float64).
+ *
+ * Data layout (env-major, agent index fastest but one):
+ *   pos, vel        Real [E][n][2]       state[:,0:2], state[:,2:4]  (drone_env.py:189)
+ *   actions         Real [E][n][2]
+ *   reward,true_r   Real [E][n]
+ *   z               Real [E][n][k+1][cols]  cols = 2 (simplify_zstate) or 5
+ *   Ni              i32  [E][n][k+1]     neighbour lists, -1 padded, Ni[..][0] == i
+ *   ncoll           i32  [E]             ordered colliding pairs (drone_env.py:284)
+ *   finished        u8   [E]
+ *   t               i32  [E]             internal_t (drone_env.py:71,256)
+ */
+#ifndef DRONESTEP_H
+#define DRONESTEP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_ABI_VERSION 1
+
+#define DS_OK 0
+#define DS_ERR_ARG (-1)         /* bad argument / unsupported shape */
+#define DS_ERR_CUDA (-2)        /* CUDA runtime error */
+#define DS_ERR_NO_DEVICE (-3)   /* no CUDA device: the library has no CPU path */
+
+#define DS_MAX_AGENTS 1024
+#define DS_MAX_K 16
+
+/* log(d_safety/d_ij) evaluation (reference drone_env.py:321,331) */
+#define DS_LOG_DIV 0    /* log(d_safety / d): same operation order as the reference */
+#define DS_LOG_DIFF 1   /* log|d_safety| - log|d|: no division, <= 4e-16 absolute difference */
+
+typedef struct ds_handle ds_handle;
+
+/* Constructor-time constants, computed by the host exactly as the reference does
+ * (generate_formation drone_env.py:115-153, delta clip :85-91).  All host float64. */
+typedef struct ds_config {
+    int32_t n_envs;          /* E */
+    int32_t n_agents;        /* n, 1..DS_MAX_AGENTS */
+    int32_t k_closest;       /* k, 0..min(n-1, DS_MAX_K)  (drone_env.py:55) */
+    int32_t simplify_zstate; /* drone_env.py:70,390 */
+    int32_t real_bytes;      /* 4 or 8 */
+    int32_t device;          /* CUDA ordinal */
+    const double *end_points; /* [n][2]  (drone_env.py:83,127-131) */
+    const double *d_safety;   /* [n]     (drone_env.py:153) */
+    const double *deltas;     /* [n]     after the clip at drone_env.py:89 */
+    const double *radius;     /* [n]     (drone_env.py:75) */
+} ds_config;
+
+/* Per-call parameters: read at every call so that attribute mutation such as
+ * `env.collision_weight = 0.2` (train_problem.py:31) keeps working. */
+typedef struct ds_params {
+    double dt;               /* drone_env.py:29  (0.05) */
+    double collision_weight; /* drone_env.py:72  (0.2)  */
+    double goal_tol;         /* drone_env.py:251 (0.2)  */
+    double sentinel;         /* drone_env.py:330 (9.99E3) */
+    double zero_eps;         /* drone_env.py:320 (-1e-6) */
+    double ghost_factor;     /* drone_env.py:386 (1.1)  */
+    int32_t max_time_steps;  /* drone_env.py:30  (200)  */
+    int32_t log_mode;        /* DS_LOG_* */
+} ds_params;
+
+/* Caller-owned device buffers of one step (layout above). */
+typedef struct ds_buffers {
+    void *pos;          /* in/out */
+    void *vel;          /* in/out */
+    void *reward;       /* out */
+    void *true_reward;  /* out */
+    void *z;            /* out */
+    int32_t *Ni;        /* out */
+    int32_t *ncoll;     /* out */
+    uint8_t *finished;  /* out (ds_step / ds_rollout only) */
+    int32_t *t;         /* in/out (ds_step / ds_rollout only) */
+} ds_buffers;
+
+/* T fused steps (episode loop of train_problem.py:82-100 without the host in
+ * between).  Environments whose done[e] != 0 are skipped; an environment that
+ * reports finished sets done[e] = 1 and stops stepping (the driver would reset
+ * it).  Trajectory pointers may each be NULL (not recorded). */
+typedef struct ds_rollout_io {
+    int32_t T;
+    int32_t n_actions;          /* rows of action_table (index mode) */
+    const void *actions;        /* Real [T][E][n][2], or NULL for index mode */
+    const uint8_t *action_idx;  /* u8 [T][E][n]: row of action_table (utils.py:262-269,307) */
+    const void *action_table;   /* Real [n_actions][2] */
+    void *pos_tr;               /* Real [T][E][n][2] */
+    void *vel_tr;               /* Real [T][E][n][2] */
+    void *reward_tr;            /* Real [T][E][n] */
+    void *true_reward_tr;       /* Real [T][E][n] */
+    void *z_tr;                 /* Real [T][E][n][k+1][cols] */
+    int32_t *Ni_tr;             /* i32 [T][E][n][k+1] */
+    int32_t *ncoll_tr;          /* i32 [T][E] */
+    uint8_t *finished_tr;       /* u8  [T][E]: 0 running, 1 finished at this step, 2 not executed */
+    double *agg;                /* f64 [E][4] in/out: sum_t mean_i r, sum_t mean_i true_r,
+                                   sum_t n_collisions, steps  (train_problem.py:98-100) */
+    uint8_t *done;              /* u8 [E] in/out */
+} ds_rollout_io;
+
+int ds_abi_version(void);
+const char *ds_last_error(void);
+/* Number of CUDA devices visible to the library (0 when there is none). */
+int ds_device_count(void);
+
+/* drones.__init__ / init_agents constants -> device (drone_env.py:55-96). */
+int ds_create(const ds_config *cfg, ds_handle **out);
+void ds_destroy(ds_handle *h);
+/* Fill *p with the reference's module constants (drone_env.py:29-30,72,...). */
+void ds_default_params(ds_params *p);
+
+/* drones.step(actions) for E environments (drone_env.py:214-258). */
+int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p,
+            const ds_buffers *io, void *cuda_stream);
+/* rewards() on the current state without integrating: the call init_agents makes
+ * after a reset (drone_env.py:208-210).  Leaves t / finished untouched. */
+int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream);
+/* T fused steps; io gives the live state and the last step's outputs. */
+int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io,
+               const ds_rollout_io *ro, void *cuda_stream);
+/* Deterministic device-side sum over environments of agg[E][4] -> out[5] (f64):
+ * the four sums and the environment count; the vector a rank all-reduces
+ * (train_problem.py:118-121).  out is caller-owned device memory. */
+int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, void *cuda_stream);
+
+/* Host-buffer variants: state[E][n][5] float64 in the reference's row layout
+ * [x, y, vx, vy, l] (drone_env.py:173,189-190). */
+int ds_set_state(ds_handle *h, const double *state_host, const int32_t *t_host,
+                 const ds_buffers *io, void *cuda_stream);
+int ds_get_state(ds_handle *h, double *state_host, int32_t *t_host,
+                 const ds_buffers *io, void *cuda_stream);
+/* env.reset() with host-chosen start positions pos[E][n][2] (random.sample of the
+ * lattice stays on the host, drone_env.py:193-205): zero velocity, t = 0, then
+ * ds_observe. */
+int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p,
+             const ds_buffers *io, void *cuda_stream);
+
+/* One step with HOST action / result buffers holding Real of the handle's
+ * precision (pinned memory recommended): H2D actions -> ds_step -> D2H of the
+ * reference's 6-tuple (drone_env.py:258), then one stream synchronise.  Output
+ * pointers may each be NULL to skip that copy.  io names the device-resident
+ * state and result buffers the step runs on. */
+typedef struct ds_host_step_out {
+    void *pos;            /* Real [E][n][2]   state[:,0:2] */
+    void *vel;            /* Real [E][n][2]   state[:,2:4] */
+    void *z;              /* Real [E][n][k+1][cols] */
+    void *reward;         /* Real [E][n] */
+    void *true_reward;    /* Real [E][n] */
+    int32_t *Ni;          /* [E][n][k+1] */
+    int32_t *ncoll;       /* [E] */
+    uint8_t *finished;    /* [E] */
+} ds_host_step_out;
+int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p,
+                 const ds_buffers *io, const ds_host_step_out *out, void *cuda_stream);
+
+/* T fused steps with a HOST action stream and HOST trajectory buffers (Real of
+ * the handle's precision; pinned memory recommended) -- the end-to-end form of
+ * the episode loop (train_problem.py:82-107): everything the loop's host side
+ * consumes comes back.  The stream is cut into chunks of `chunk` steps (0 = let
+ * the library choose); chunk c+1's H2D copy and chunk c-1's D2H copy overlap
+ * chunk c's kernel on two library-owned copy streams, with double-buffered
+ * staging owned by the handle.  Trajectory pointers may each be NULL.  Runs from
+ * the state in io with done = 0 and agg = 0; returns after one synchronise. */
+typedef struct ds_host_rollout {
+    int32_t T;
+    int32_t chunk;
+    int32_t n_actions;
+    int32_t _pad;
+    const void *actions;        /* host Real [T][E][n][2], or NULL for index mode */
+    const uint8_t *action_idx;  /* host u8 [T][E][n] */
+    const void *action_table;   /* host Real [n_actions][2] */
+    void *pos_tr;               /* host, layouts as in ds_rollout_io */
+    void *vel_tr;
+    void *reward_tr;
+    void *true_reward_tr;
+    void *z_tr;
+    int32_t *Ni_tr;
+    int32_t *ncoll_tr;
+    uint8_t *finished_tr;
+    double *agg;                /* host f64 [E][4] out (may be NULL) */
+} ds_host_rollout;
+int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io,
+                    const ds_host_rollout *hr, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRONESTEP_H */

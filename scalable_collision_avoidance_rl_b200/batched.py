@@ -1,0 +1,322 @@
+"""BatchedDrones: E independent drone environments stepped by one fused CUDA kernel.
+
+Host-side mirror of the reference's ``drone_env.drones`` for a batch of
+environments (reference drone_env.py:53-401).  Python/PyTorch here only own the
+device memory and the CUDA stream; every step / observation / rollout goes
+through the C ABI of ``libdronestep.so`` (include/dronestep.h).  There is no CPU
+implementation: constructing a BatchedDrones without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, formation
+
+_REAL = {torch.float64: 8, torch.float32: 4}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class BatchedDrones:
+    """E environments x n agents, env-major SoA tensors on one GPU.
+
+    Tensors (all caller-visible, updated in place by every call):
+      pos, vel [E,n,2] | rewards, true_rewards [E,n] | z_states [E,n,k+1,cols]
+      Ni [E,n,k+1] int32 (-1 padded) | n_collisions [E] int32 | finished [E] uint8
+      internal_t [E] int32
+    """
+
+    def __init__(self, n_envs: int, n_agents: int, grid, end_formation: str = "O", k_closest: int = 2,
+                 deltas=None, simplify_zstate: bool = False, dtype=torch.float64, device=None,
+                 seed: int | None = None, start_positions=None, warn=True, constants=None):
+        if not torch.cuda.is_available():
+            raise _lib.DroneStepError(
+                "BatchedDrones needs a CUDA device: the step path exists only as sm_100a kernels "
+                "(libdronestep.so); there is no CPU fallback")
+        if dtype not in _REAL:
+            raise ValueError("dtype must be torch.float64 (parity) or torch.float32 (throughput)")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = dtype
+        self.n_envs, self.n_agents, self.k_closest = int(n_envs), int(n_agents), int(k_closest)
+        self.simplify_zstate = bool(simplify_zstate)
+        self.grid = list(grid)
+        self.collision_weight = 0.2                       # drone_env.py:72 (mutable attribute)
+        self.dt = 0.05                                    # drone_env.py:29
+        self.max_time_steps = 200                         # drone_env.py:30
+        self.log_mode = _lib.DS_LOG_DIV
+        self.drone_radius = np.ones(self.n_agents) * formation.DRONE_RADIUS
+        if constants is not None:
+            # (end_points, d_safety, deltas) given verbatim, e.g. by drones.rewards()
+            self.end_points = np.asarray(constants[0], np.float64).reshape(-1, 1)
+            self.d_safety = np.asarray(constants[1], np.float64).reshape(-1)
+            self.deltas, clipped = np.asarray(constants[2], np.float64).reshape(-1), False
+        else:
+            self.end_points = formation.end_formation(end_formation, self.n_agents, self.grid)
+            self.d_safety = formation.safety_distances(self.end_points, self.drone_radius)
+            self.deltas, clipped = formation.clip_deltas(deltas, self.d_safety)
+        if clipped and warn:
+            print("Some deltas are greater than the final minimum distance between end positions. "
+                  "Using minimum distance between end positions for those cases instead.",
+                  f"deltas = {self.deltas}")
+        self.local_state_space = formation.local_state_space(self.k_closest, self.simplify_zstate)
+        self.local_action_space = formation.DIM
+        self.cols = 2 if self.simplify_zstate else 5
+        self._rng = np.random.default_rng(seed)
+
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        dev, dt_ = self.device, self.dtype
+        self.pos = torch.zeros((E, n, 2), dtype=dt_, device=dev)
+        self.vel = torch.zeros((E, n, 2), dtype=dt_, device=dev)
+        self.rewards = torch.zeros((E, n), dtype=dt_, device=dev)
+        self.true_rewards = torch.zeros((E, n), dtype=dt_, device=dev)
+        self.z_states = torch.zeros((E, n, k + 1, self.cols), dtype=dt_, device=dev)
+        self.Ni = torch.full((E, n, k + 1), -1, dtype=torch.int32, device=dev)
+        self.n_collisions = torch.zeros(E, dtype=torch.int32, device=dev)
+        self.finished = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.internal_t = torch.zeros(E, dtype=torch.int32, device=dev)
+        self.done = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.agg = torch.zeros((E, 4), dtype=torch.float64, device=dev)
+        self._agg_sum = torch.zeros(5, dtype=torch.float64, device=dev)
+
+        # constants -> device (ds_create)
+        self._c_xF = np.ascontiguousarray(self.end_points.reshape(-1), np.float64)
+        self._c_ds = np.ascontiguousarray(self.d_safety, np.float64)
+        self._c_dl = np.ascontiguousarray(np.asarray(self.deltas, np.float64).reshape(-1))
+        self._c_rad = np.ascontiguousarray(self.drone_radius, np.float64)
+        if self._c_dl.shape[0] != n:
+            raise ValueError("deltas must have one entry per agent")
+        cfg = _lib.ds_config(E, n, k, int(self.simplify_zstate), _REAL[dt_], self.device.index or 0,
+                             self._c_xF.ctypes.data, self._c_ds.ctypes.data, self._c_dl.ctypes.data,
+                             self._c_rad.ctypes.data)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.ds_create(ctypes.byref(cfg), ctypes.byref(self._h)), "ds_create")
+        self._io = _lib.ds_buffers(self.pos.data_ptr(), self.vel.data_ptr(), self.rewards.data_ptr(),
+                                   self.true_rewards.data_ptr(), self.z_states.data_ptr(),
+                                   self.Ni.data_ptr(), self.n_collisions.data_ptr(),
+                                   self.finished.data_ptr(), self.internal_t.data_ptr())
+        self._pinned = {}
+        self.reset(start_positions)
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.ds_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _params(self):
+        return _lib.ds_params(self.dt, float(self.collision_weight), 0.2, 9.99e3, -10 ** -6, 1.1,
+                              int(self.max_time_steps), int(self.log_mode))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _pin(self, name, shape, dtype):
+        buf = self._pinned.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[name] = buf
+        return buf
+
+    # ------------------------------------------------------------------ reset / state
+    def reset(self, start_positions=None):
+        """drones.reset() (drone_env.py:98-102) for all E environments: distinct lattice
+        nodes, zero velocity, t = 0, then the observation of the start state."""
+        E, n = self.n_envs, self.n_agents
+        if start_positions is None:
+            start_positions = formation.sample_start_batched(E, n, self.grid, self._rng)
+        sp = np.ascontiguousarray(np.asarray(start_positions, np.float64).reshape(E, n, 2))
+        p = self._params()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ds_reset(self._h, sp.ctypes.data_as(ctypes.c_void_p), ctypes.byref(p),
+                                         ctypes.byref(self._io), self._stream()), "ds_reset")
+        self.done.zero_()
+        self.agg.zero_()
+
+    def observe(self):
+        """rewards() on the current state (drone_env.py:208): refresh z_states/Ni/rewards."""
+        p = self._params()
+        _lib.check(self.lib.ds_observe(self._h, ctypes.byref(p), ctypes.byref(self._io), self._stream()),
+                   "ds_observe")
+
+    def set_state(self, state, internal_t=None):
+        """state[E,n,5] rows [x,y,vx,vy,l] (host float64) -> device; observation NOT refreshed."""
+        st = np.ascontiguousarray(np.asarray(state, np.float64).reshape(self.n_envs, self.n_agents, 5))
+        tt = None
+        if internal_t is not None:
+            tt = np.ascontiguousarray(np.broadcast_to(np.asarray(internal_t, np.int32), (self.n_envs,)))
+        _lib.check(self.lib.ds_set_state(self._h, st.ctypes.data_as(ctypes.c_void_p),
+                                         None if tt is None else tt.ctypes.data_as(ctypes.c_void_p),
+                                         ctypes.byref(self._io), self._stream()), "ds_set_state")
+
+    def get_state(self):
+        st = np.empty((self.n_envs, self.n_agents, 5))
+        tt = np.empty(self.n_envs, np.int32)
+        _lib.check(self.lib.ds_get_state(self._h, st.ctypes.data_as(ctypes.c_void_p),
+                                         tt.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self._io),
+                                         self._stream()), "ds_get_state")
+        return st, tt
+
+    @property
+    def state(self):
+        """[E,n,5] device tensor [x,y,vx,vy,l] assembled from the SoA buffers."""
+        rad = torch.as_tensor(self.drone_radius, dtype=self.dtype, device=self.device)
+        return torch.cat([self.pos, self.vel, rad.expand(self.n_envs, -1).unsqueeze(-1)], dim=2)
+
+    # ------------------------------------------------------------------ step
+    def step(self, actions):
+        """drones.step(actions) for every environment (drone_env.py:214-258).
+
+        actions: device tensor [E,n,2] of this env's dtype.  Returns the reference's
+        6-tuple as device tensors (views of the live buffers, like the reference's aliasing):
+        (state-as-(pos,vel), z_states, rewards, n_collisions, finished, true_rewards).
+        """
+        if not (isinstance(actions, torch.Tensor) and actions.is_cuda):
+            raise TypeError("step() takes a CUDA tensor; use step_host() for host arrays")
+        a = actions.to(self.dtype).reshape(self.n_envs, self.n_agents, 2).contiguous()
+        p = self._params()
+        _lib.check(self.lib.ds_step(self._h, _ptr(a), ctypes.byref(p), ctypes.byref(self._io),
+                                    self._stream()), "ds_step")
+        return ((self.pos, self.vel), self.z_states, self.rewards, self.n_collisions, self.finished,
+                self.true_rewards)
+
+    def step_host(self, actions):
+        """Same step with HOST arrays in and out (ds_step_host): one H2D, one kernel, D2H of the
+        reference's 6-tuple into pinned buffers, one synchronise.  Returns numpy views."""
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        a = self._pin("act", (E, n, 2), self.dtype)
+        a.numpy()[...] = np.asarray(actions).reshape(E, n, 2)
+        o = dict(pos=self._pin("pos", (E, n, 2), self.dtype), vel=self._pin("vel", (E, n, 2), self.dtype),
+                 z=self._pin("z", (E, n, k + 1, self.cols), self.dtype),
+                 r=self._pin("r", (E, n), self.dtype), tr=self._pin("tr", (E, n), self.dtype),
+                 Ni=self._pin("Ni", (E, n, k + 1), torch.int32), nc=self._pin("nc", (E,), torch.int32),
+                 fin=self._pin("fin", (E,), torch.uint8))
+        out = _lib.ds_host_step_out(o["pos"].data_ptr(), o["vel"].data_ptr(), o["z"].data_ptr(),
+                                    o["r"].data_ptr(), o["tr"].data_ptr(), o["Ni"].data_ptr(),
+                                    o["nc"].data_ptr(), o["fin"].data_ptr())
+        p = self._params()
+        _lib.check(self.lib.ds_step_host(self._h, _ptr(a), ctypes.byref(p), ctypes.byref(self._io),
+                                         ctypes.byref(out), self._stream()), "ds_step_host")
+        return {k_: v.numpy() for k_, v in o.items()}
+
+    # ------------------------------------------------------------------ rollout
+    def rollout(self, actions=None, action_idx=None, action_table=None, record=("reward", "true_reward",
+                "ncoll", "finished"), out=None):
+        """T fused steps in ONE launch (ds_rollout).
+
+        actions [T,E,n,2] device tensor, or action_idx [T,E,n] uint8 + action_table [A,2].
+        record: names among pos, vel, reward, true_reward, obs (z + Ni), ncoll, finished.
+        Returns a dict of device trajectory tensors plus 'agg' [E,4] and 'done' [E].
+        """
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        if actions is not None:
+            actions = actions.to(self.dtype).contiguous()
+            T = actions.shape[0]
+            assert tuple(actions.shape) == (T, E, n, 2)
+        else:
+            action_idx = action_idx.contiguous()
+            T = action_idx.shape[0]
+            assert action_idx.dtype == torch.uint8 and tuple(action_idx.shape) == (T, E, n)
+            action_table = torch.as_tensor(action_table, dtype=self.dtype, device=self.device).contiguous()
+        out = {} if out is None else out
+        dev, dt_ = self.device, self.dtype
+
+        def buf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+
+        rec = set(record)
+        ro = _lib.ds_rollout_io()
+        ro.T = T
+        ro.n_actions = 0 if action_table is None else int(action_table.shape[0])
+        ro.actions = None if actions is None else actions.data_ptr()
+        ro.action_idx = None if action_idx is None else action_idx.data_ptr()
+        ro.action_table = None if action_table is None else action_table.data_ptr()
+        if "pos" in rec: ro.pos_tr = buf("pos", (T, E, n, 2), dt_).data_ptr()
+        if "vel" in rec: ro.vel_tr = buf("vel", (T, E, n, 2), dt_).data_ptr()
+        if "reward" in rec: ro.reward_tr = buf("reward", (T, E, n), dt_).data_ptr()
+        if "true_reward" in rec: ro.true_reward_tr = buf("true_reward", (T, E, n), dt_).data_ptr()
+        if "obs" in rec:
+            ro.z_tr = buf("z", (T, E, n, k + 1, self.cols), dt_).data_ptr()
+            ro.Ni_tr = buf("Ni", (T, E, n, k + 1), torch.int32).data_ptr()
+        if "ncoll" in rec: ro.ncoll_tr = buf("ncoll", (T, E), torch.int32).data_ptr()
+        if "finished" in rec: ro.finished_tr = buf("finished", (T, E), torch.uint8).data_ptr()
+        ro.agg = self.agg.data_ptr()
+        ro.done = self.done.data_ptr()
+        p = self._params()
+        _lib.check(self.lib.ds_rollout(self._h, ctypes.byref(p), ctypes.byref(self._io), ctypes.byref(ro),
+                                       self._stream()), "ds_rollout")
+        out["agg"], out["done"] = self.agg, self.done
+        return out
+
+    def rollout_host(self, actions=None, action_idx=None, action_table=None,
+                     record=("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished"),
+                     chunk=0, out=None):
+        """End-to-end episode loop with HOST buffers (ds_rollout_host): pinned host action stream
+        in, pinned host trajectories out, copies pipelined against the kernel.  `actions` /
+        `action_idx` must be pinned CPU tensors (or are copied into pinned staging)."""
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        hr = _lib.ds_host_rollout()
+        keep = []
+        if actions is not None:
+            a = actions if (isinstance(actions, torch.Tensor) and actions.is_pinned()) else None
+            if a is None:
+                a = self._pin("ro_act", tuple(np.shape(actions)), self.dtype)
+                a.copy_(torch.as_tensor(np.asarray(actions)))
+            T = a.shape[0]
+            hr.actions = a.data_ptr(); keep.append(a)
+        else:
+            a = action_idx if (isinstance(action_idx, torch.Tensor) and action_idx.is_pinned()) else None
+            if a is None:
+                a = self._pin("ro_aidx", tuple(np.shape(action_idx)), torch.uint8)
+                a.copy_(torch.as_tensor(np.asarray(action_idx)))
+            T = a.shape[0]
+            tab = torch.as_tensor(np.asarray(action_table), dtype=self.dtype).contiguous()
+            hr.action_idx = a.data_ptr(); hr.action_table = tab.data_ptr(); hr.n_actions = tab.shape[0]
+            keep += [a, tab]
+        hr.T, hr.chunk = T, int(chunk)
+        out = {} if out is None else out
+        rec = set(record)
+
+        def hbuf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = torch.empty(shape, dtype=dtype, pin_memory=True)
+                out[name] = t
+            return t.data_ptr()
+
+        dt_ = self.dtype
+        if "pos" in rec: hr.pos_tr = hbuf("pos", (T, E, n, 2), dt_)
+        if "vel" in rec: hr.vel_tr = hbuf("vel", (T, E, n, 2), dt_)
+        if "reward" in rec: hr.reward_tr = hbuf("reward", (T, E, n), dt_)
+        if "true_reward" in rec: hr.true_reward_tr = hbuf("true_reward", (T, E, n), dt_)
+        if "obs" in rec:
+            hr.z_tr = hbuf("z", (T, E, n, k + 1, self.cols), dt_)
+            hr.Ni_tr = hbuf("Ni", (T, E, n, k + 1), torch.int32)
+        if "ncoll" in rec: hr.ncoll_tr = hbuf("ncoll", (T, E), torch.int32)
+        if "finished" in rec: hr.finished_tr = hbuf("finished", (T, E), torch.uint8)
+        hr.agg = hbuf("agg", (E, 4), torch.float64)
+        p = self._params()
+        _lib.check(self.lib.ds_rollout_host(self._h, ctypes.byref(p), ctypes.byref(self._io),
+                                            ctypes.byref(hr), self._stream()), "ds_rollout_host")
+        return out
+
+    def episode_aggregates(self):
+        """Device-side sum over this rank's environments of the per-env episode accumulators
+        -> float64 [5] = (sum_t mean_i r, sum_t mean_i true_r, sum_t collisions, steps, #envs):
+        the vector a rank all-reduces (train_problem.py:98-100,118-121)."""
+        _lib.check(self.lib.ds_reduce_aggregates(self._h, _ptr(self.agg), _ptr(self._agg_sum),
+                                                 self._stream()), "ds_reduce_aggregates")
+        return self._agg_sum

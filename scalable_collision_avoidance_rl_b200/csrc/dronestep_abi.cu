@@ -1,0 +1,581 @@
+// dronestep_abi.cu -- extern "C" boundary of libdronestep.so (see include/dronestep.h).
+//
+// Host side of the fused kernels in dronestep_kernels.cuh: argument checking,
+// constant upload, launch geometry, and the host-buffer convenience entries.
+// There is deliberately NO CPU implementation behind this boundary: without a
+// CUDA device every compute entry fails with DS_ERR_NO_DEVICE.
+#include "../../include/dronestep.h"
+#include "dronestep_kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define DS_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail(DS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));   \
+    } while (0)
+
+}  // namespace
+
+struct ds_handle {
+    int E, n, k, simplify, real_bytes, device;
+    int sm_count;
+    // launch geometry
+    int mode;                 // 0 warp groups, 1 CTA <= 256 threads, 2 CTA <= 1024 threads
+    int epg, threads, blocks;
+    size_t smem;
+    // device constants (Real typed)
+    void *d_xF, *d_ds, *d_delta, *d_radius, *d_logds;
+    std::vector<double> h_radius;
+    // staging for the host-buffer entries
+    void *act_stage;
+    size_t act_stage_bytes;
+    // ds_rollout_host: two staging slots, two copy streams, events
+    struct Slot {
+        void *act = nullptr; uint8_t *aidx = nullptr;
+        void *pos = nullptr, *vel = nullptr, *r = nullptr, *tr = nullptr, *z = nullptr;
+        int32_t *Ni = nullptr, *ncoll = nullptr; uint8_t *fin = nullptr;
+        cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
+    } slot[2];
+    int slot_chunk = 0;           // steps the slots are sized for
+    unsigned slot_mask = 0;       // which trajectory buffers the slots hold
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    double *d_agg = nullptr; uint8_t *d_done = nullptr; void *d_atable = nullptr;
+};
+
+namespace {
+
+template <typename Real>
+int upload_consts(ds_handle *h, const ds_config *cfg)
+{
+    const int n = h->n;
+    std::vector<Real> xF(2 * n), dsv(n), dl(n), rd(n), lg(n);
+    for (int i = 0; i < n; ++i) {
+        xF[2 * i] = (Real)cfg->end_points[2 * i];
+        xF[2 * i + 1] = (Real)cfg->end_points[2 * i + 1];
+        dsv[i] = (Real)cfg->d_safety[i];
+        dl[i] = (Real)cfg->deltas[i];
+        rd[i] = (Real)cfg->radius[i];
+        lg[i] = (Real)std::log(std::fabs(cfg->d_safety[i]));
+    }
+    DS_CUDA(cudaMalloc(&h->d_xF, sizeof(Real) * 2 * n));
+    DS_CUDA(cudaMalloc(&h->d_ds, sizeof(Real) * n));
+    DS_CUDA(cudaMalloc(&h->d_delta, sizeof(Real) * n));
+    DS_CUDA(cudaMalloc(&h->d_radius, sizeof(Real) * n));
+    DS_CUDA(cudaMalloc(&h->d_logds, sizeof(Real) * n));
+    DS_CUDA(cudaMemcpy(h->d_xF, xF.data(), sizeof(Real) * 2 * n, cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(h->d_ds, dsv.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(h->d_delta, dl.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(h->d_radius, rd.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(h->d_logds, lg.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
+    return DS_OK;
+}
+
+void plan_launch(ds_handle *h)
+{
+    const int n = h->n;
+    h->mode = n <= 32 ? 0 : (n <= 256 ? 1 : 2);
+    if (h->mode == 0) {
+        h->epg = 32 / n;                       // whole environments per warp
+        h->threads = 128;                      // 4 warps (groups) per CTA
+        const long long groups = ((long long)h->E + h->epg - 1) / h->epg;
+        h->blocks = (int)((groups + 3) / 4);
+    } else {
+        h->epg = 256 / n > 0 ? 256 / n : 1;    // whole environments per CTA
+        h->threads = ((h->epg * n + 31) / 32) * 32;
+        h->blocks = (int)(((long long)h->E + h->epg - 1) / h->epg);
+    }
+    const int gpb = h->mode == 0 ? 4 : 1;
+    if (h->real_bytes == 8)
+        h->smem = ds::GroupSmem<double>::const_bytes(n) + ds::GroupSmem<double>::group_bytes(h->epg, n) * gpb;
+    else
+        h->smem = ds::GroupSmem<float>::const_bytes(n) + ds::GroupSmem<float>::group_bytes(h->epg, n) * gpb;
+    if (h->blocks < 1) h->blocks = 1;
+}
+
+int check_params(const ds_params *p)
+{
+    if (!p) return fail(DS_ERR_ARG, "ds_params is NULL");
+    if (p->log_mode != DS_LOG_DIV && p->log_mode != DS_LOG_DIFF)
+        return fail(DS_ERR_ARG, "ds_params.log_mode must be DS_LOG_DIV or DS_LOG_DIFF");
+    if (p->max_time_steps < 1) return fail(DS_ERR_ARG, "ds_params.max_time_steps < 1");
+    return DS_OK;
+}
+
+int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const void *act,
+                   bool integrate, ds::StepArgs *a)
+{
+    if (!h) return fail(DS_ERR_ARG, "handle is NULL");
+    if (int rc = check_params(p)) return rc;
+    if (!io) return fail(DS_ERR_ARG, "ds_buffers is NULL");
+    if (!io->pos || !io->vel || !io->reward || !io->true_reward || !io->z || !io->Ni || !io->ncoll)
+        return fail(DS_ERR_ARG, "ds_buffers: pos/vel/reward/true_reward/z/Ni/ncoll must be non-NULL");
+    if (integrate && (!io->finished || !io->t))
+        return fail(DS_ERR_ARG, "ds_buffers: finished/t must be non-NULL for a step");
+    a->E = h->E; a->n = h->n; a->k = h->k; a->simplify = h->simplify; a->epg = h->epg;
+    a->do_integrate = integrate ? 1 : 0;
+    a->log_mode = p->log_mode;
+    a->max_steps = p->max_time_steps;
+    a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds};
+    a->dt = p->dt;
+    a->q = 2 * p->dt;                        // drone_env.py:269
+    a->b = p->collision_weight * p->dt;      // drone_env.py:270
+    a->goal_tol = p->goal_tol; a->sentinel = p->sentinel; a->zero_eps = p->zero_eps;
+    a->ghost = p->ghost_factor;
+    a->act = act;
+    a->pos = io->pos; a->vel = io->vel; a->r = io->reward; a->tr = io->true_reward; a->z = io->z;
+    a->Ni = io->Ni; a->ncoll = io->ncoll; a->fin = io->finished; a->t = io->t;
+    return DS_OK;
+}
+
+template <typename KernelT, typename ArgsT>
+int launch(ds_handle *h, KernelT kernel, const ArgsT &args, cudaStream_t st)
+{
+    if (h->smem > 48 * 1024)
+        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    kernel<<<h->blocks, h->threads, h->smem, st>>>(args);
+    DS_CUDA(cudaGetLastError());
+    return DS_OK;
+}
+
+#define DS_DISPATCH_K(KERNEL, REAL, MODE, ARGS)                                           \
+    switch (h->k) {                                                                      \
+    case 0: return launch(h, ds::KERNEL<REAL, 0, MODE>, ARGS, st);                       \
+    case 1: return launch(h, ds::KERNEL<REAL, 1, MODE>, ARGS, st);                       \
+    case 2: return launch(h, ds::KERNEL<REAL, 2, MODE>, ARGS, st);                       \
+    case 3: return launch(h, ds::KERNEL<REAL, 3, MODE>, ARGS, st);                       \
+    case 4: return launch(h, ds::KERNEL<REAL, 4, MODE>, ARGS, st);                       \
+    default: return launch(h, ds::KERNEL<REAL, -1, MODE>, ARGS, st);                     \
+    }
+
+#define DS_DISPATCH_MODE(KERNEL, REAL, ARGS)                                              \
+    if (h->mode == 0) { DS_DISPATCH_K(KERNEL, REAL, 0, ARGS) }                            \
+    else if (h->mode == 1) { DS_DISPATCH_K(KERNEL, REAL, 1, ARGS) }                       \
+    else { DS_DISPATCH_K(KERNEL, REAL, 2, ARGS) }
+
+int launch_step(ds_handle *h, const ds::StepArgs &a, cudaStream_t st)
+{
+    if (h->real_bytes == 8) { DS_DISPATCH_MODE(step_kernel, double, a) }
+    else { DS_DISPATCH_MODE(step_kernel, float, a) }
+}
+
+int launch_rollout(ds_handle *h, const ds::RolloutArgs &a, cudaStream_t st)
+{
+    if (h->real_bytes == 8) { DS_DISPATCH_MODE(rollout_kernel, double, a) }
+    else { DS_DISPATCH_MODE(rollout_kernel, float, a) }
+}
+
+void free_slots(ds_handle *h)
+{
+    for (auto &s : h->slot) {
+        cudaFree(s.act); cudaFree(s.aidx); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.r);
+        cudaFree(s.tr); cudaFree(s.z); cudaFree(s.Ni); cudaFree(s.ncoll); cudaFree(s.fin);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.kernel_done) cudaEventDestroy(s.kernel_done);
+        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
+        s = ds_handle::Slot();
+    }
+    h->slot_chunk = 0; h->slot_mask = 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ds_abi_version(void) { return DS_ABI_VERSION; }
+
+const char *ds_last_error(void) { return g_err.c_str(); }
+
+int ds_device_count(void)
+{
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+void ds_default_params(ds_params *p)
+{
+    if (!p) return;
+    p->dt = 0.05;
+    p->collision_weight = 0.2;
+    p->goal_tol = 0.2;
+    p->sentinel = 9.99E3;
+    p->zero_eps = -1e-6;
+    p->ghost_factor = 1.1;
+    p->max_time_steps = 200;
+    p->log_mode = DS_LOG_DIV;
+}
+
+int ds_create(const ds_config *cfg, ds_handle **out)
+{
+    if (!cfg || !out) return fail(DS_ERR_ARG, "ds_create: NULL argument");
+    *out = nullptr;
+    if (cfg->n_envs < 1) return fail(DS_ERR_ARG, "ds_create: n_envs < 1");
+    if (cfg->n_agents < 1 || cfg->n_agents > DS_MAX_AGENTS)
+        return fail(DS_ERR_ARG, "ds_create: n_agents out of range [1, DS_MAX_AGENTS]");
+    if (cfg->k_closest < 0 || cfg->k_closest > DS_MAX_K || cfg->k_closest >= cfg->n_agents)
+        return fail(DS_ERR_ARG, "ds_create: k_closest must satisfy 0 <= k <= min(n_agents-1, DS_MAX_K)");
+    if (cfg->real_bytes != 4 && cfg->real_bytes != 8)
+        return fail(DS_ERR_ARG, "ds_create: real_bytes must be 4 or 8");
+    if (!cfg->end_points || !cfg->d_safety || !cfg->deltas || !cfg->radius)
+        return fail(DS_ERR_ARG, "ds_create: constant arrays must be non-NULL");
+    const int ndev = ds_device_count();
+    if (ndev < 1)
+        return fail(DS_ERR_NO_DEVICE, "ds_create: no CUDA device visible; libdronestep has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(DS_ERR_ARG, "ds_create: bad device ordinal");
+    DeviceGuard guard(cfg->device);
+    if (!guard.ok) return fail(DS_ERR_CUDA, "ds_create: cudaSetDevice failed");
+
+    ds_handle *h = new ds_handle();
+    h->E = cfg->n_envs; h->n = cfg->n_agents; h->k = cfg->k_closest;
+    h->simplify = cfg->simplify_zstate ? 1 : 0;
+    h->real_bytes = cfg->real_bytes; h->device = cfg->device;
+    h->d_xF = h->d_ds = h->d_delta = h->d_radius = h->d_logds = nullptr;
+    h->act_stage = nullptr; h->act_stage_bytes = 0;
+    h->h_radius.assign(cfg->radius, cfg->radius + cfg->n_agents);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) {
+        delete h;
+        return fail(DS_ERR_CUDA, "ds_create: cudaGetDeviceProperties failed");
+    }
+    h->sm_count = prop.multiProcessorCount;
+    plan_launch(h);
+    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        delete h;
+        return fail(DS_ERR_ARG, "ds_create: shared-memory footprint exceeds the device limit");
+    }
+    const int rc = (h->real_bytes == 8) ? upload_consts<double>(h, cfg) : upload_consts<float>(h, cfg);
+    if (rc != DS_OK) { ds_destroy(h); return rc; }
+    *out = h;
+    return DS_OK;
+}
+
+void ds_destroy(ds_handle *h)
+{
+    if (!h) return;
+    DeviceGuard guard(h->device);
+    cudaFree(h->d_xF); cudaFree(h->d_ds); cudaFree(h->d_delta); cudaFree(h->d_radius);
+    cudaFree(h->d_logds); cudaFree(h->act_stage);
+    free_slots(h);
+    cudaFree(h->d_agg); cudaFree(h->d_done); cudaFree(h->d_atable);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+}
+
+int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p, const ds_buffers *io,
+            void *cuda_stream)
+{
+    ds::StepArgs a;
+    if (int rc = fill_step_args(h, p, io, actions_dev, true, &a)) return rc;
+    if (!actions_dev) return fail(DS_ERR_ARG, "ds_step: actions_dev is NULL");
+    DeviceGuard guard(h->device);
+    return launch_step(h, a, (cudaStream_t)cuda_stream);
+}
+
+int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream)
+{
+    ds::StepArgs a;
+    if (int rc = fill_step_args(h, p, io, nullptr, false, &a)) return rc;
+    DeviceGuard guard(h->device);
+    return launch_step(h, a, (cudaStream_t)cuda_stream);
+}
+
+int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_rollout_io *ro,
+               void *cuda_stream)
+{
+    ds::RolloutArgs ra;
+    if (int rc = fill_step_args(h, p, io, nullptr, true, &ra.s)) return rc;
+    if (!ro) return fail(DS_ERR_ARG, "ds_rollout: ds_rollout_io is NULL");
+    if (ro->T < 0) return fail(DS_ERR_ARG, "ds_rollout: T < 0");
+    if (!ro->agg || !ro->done) return fail(DS_ERR_ARG, "ds_rollout: agg/done must be non-NULL");
+    if (!ro->actions) {
+        if (!ro->action_idx || !ro->action_table || ro->n_actions < 1 || ro->n_actions > 256)
+            return fail(DS_ERR_ARG, "ds_rollout: give actions, or action_idx + action_table (1..256 rows)");
+    }
+    if ((ro->z_tr == nullptr) != (ro->Ni_tr == nullptr))
+        return fail(DS_ERR_ARG, "ds_rollout: z_tr and Ni_tr must be given together");
+    ra.T = ro->T; ra.n_actions = ro->n_actions;
+    ra.actions = ro->actions; ra.aidx = ro->action_idx; ra.atable = ro->action_table;
+    ra.pos_tr = ro->pos_tr; ra.vel_tr = ro->vel_tr; ra.r_tr = ro->reward_tr; ra.tr_tr = ro->true_reward_tr;
+    ra.z_tr = ro->z_tr; ra.Ni_tr = ro->Ni_tr; ra.ncoll_tr = ro->ncoll_tr; ra.fin_tr = ro->finished_tr;
+    ra.agg = ro->agg; ra.done = ro->done;
+    if (ro->T == 0) return DS_OK;
+    DeviceGuard guard(h->device);
+    return launch_rollout(h, ra, (cudaStream_t)cuda_stream);
+}
+
+int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, void *cuda_stream)
+{
+    if (!h || !agg_dev || !out_dev) return fail(DS_ERR_ARG, "ds_reduce_aggregates: NULL argument");
+    DeviceGuard guard(h->device);
+    ds::reduce_agg_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(agg_dev, h->E, out_dev);
+    DS_CUDA(cudaGetLastError());
+    return DS_OK;
+}
+
+int ds_set_state(ds_handle *h, const double *state_host, const int32_t *t_host, const ds_buffers *io,
+                 void *cuda_stream)
+{
+    if (!h || !state_host || !io || !io->pos || !io->vel)
+        return fail(DS_ERR_ARG, "ds_set_state: NULL argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t A = (size_t)h->E * h->n;
+    const size_t bytes = A * 2 * h->real_bytes;
+    std::vector<unsigned char> pos(bytes), vel(bytes);
+    for (size_t a = 0; a < A; ++a) {
+        const double *row = state_host + a * 5;
+        if (h->real_bytes == 8) {
+            double *pp = (double *)pos.data() + 2 * a, *vv = (double *)vel.data() + 2 * a;
+            pp[0] = row[0]; pp[1] = row[1]; vv[0] = row[2]; vv[1] = row[3];
+        } else {
+            float *pp = (float *)pos.data() + 2 * a, *vv = (float *)vel.data() + 2 * a;
+            pp[0] = (float)row[0]; pp[1] = (float)row[1]; vv[0] = (float)row[2]; vv[1] = (float)row[3];
+        }
+    }
+    DS_CUDA(cudaMemcpyAsync(io->pos, pos.data(), bytes, cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemcpyAsync(io->vel, vel.data(), bytes, cudaMemcpyHostToDevice, st));
+    if (t_host && io->t)
+        DS_CUDA(cudaMemcpyAsync(io->t, t_host, sizeof(int32_t) * h->E, cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    return DS_OK;
+}
+
+int ds_get_state(ds_handle *h, double *state_host, int32_t *t_host, const ds_buffers *io,
+                 void *cuda_stream)
+{
+    if (!h || !state_host || !io || !io->pos || !io->vel)
+        return fail(DS_ERR_ARG, "ds_get_state: NULL argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t A = (size_t)h->E * h->n;
+    const size_t bytes = A * 2 * h->real_bytes;
+    std::vector<unsigned char> pos(bytes), vel(bytes);
+    DS_CUDA(cudaMemcpyAsync(pos.data(), io->pos, bytes, cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaMemcpyAsync(vel.data(), io->vel, bytes, cudaMemcpyDeviceToHost, st));
+    if (t_host && io->t)
+        DS_CUDA(cudaMemcpyAsync(t_host, io->t, sizeof(int32_t) * h->E, cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    for (size_t a = 0; a < A; ++a) {
+        double *row = state_host + a * 5;
+        if (h->real_bytes == 8) {
+            const double *pp = (const double *)pos.data() + 2 * a, *vv = (const double *)vel.data() + 2 * a;
+            row[0] = pp[0]; row[1] = pp[1]; row[2] = vv[0]; row[3] = vv[1];
+        } else {
+            const float *pp = (const float *)pos.data() + 2 * a, *vv = (const float *)vel.data() + 2 * a;
+            row[0] = pp[0]; row[1] = pp[1]; row[2] = vv[0]; row[3] = vv[1];
+        }
+        row[4] = h->h_radius[a % h->n];
+    }
+    return DS_OK;
+}
+
+int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p, const ds_buffers *io,
+             void *cuda_stream)
+{
+    if (!h || !pos_host || !io || !io->pos || !io->vel)
+        return fail(DS_ERR_ARG, "ds_reset: NULL argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t A = (size_t)h->E * h->n;
+    const size_t bytes = A * 2 * h->real_bytes;
+    std::vector<float> tmp;
+    const void *src = pos_host;
+    if (h->real_bytes == 4) {
+        tmp.resize(A * 2);
+        for (size_t a = 0; a < 2 * A; ++a) tmp[a] = (float)pos_host[a];
+        src = tmp.data();
+    }
+    DS_CUDA(cudaMemcpyAsync(io->pos, src, bytes, cudaMemcpyHostToDevice, st));
+    DS_CUDA(cudaMemsetAsync(io->vel, 0, bytes, st));
+    if (io->t) DS_CUDA(cudaMemsetAsync(io->t, 0, sizeof(int32_t) * h->E, st));
+    if (io->finished) DS_CUDA(cudaMemsetAsync(io->finished, 0, h->E, st));
+    DS_CUDA(cudaStreamSynchronize(st));   // tmp must outlive the copy
+    return ds_observe(h, p, io, cuda_stream);
+}
+
+int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,
+                 const ds_host_step_out *out, void *cuda_stream)
+{
+    if (!h || !actions_host || !out) return fail(DS_ERR_ARG, "ds_step_host: NULL argument");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t A = (size_t)h->E * h->n;
+    const size_t rb = h->real_bytes;
+    const size_t act_bytes = A * 2 * rb;
+    if (h->act_stage_bytes < act_bytes) {
+        cudaFree(h->act_stage);
+        h->act_stage = nullptr; h->act_stage_bytes = 0;
+        DS_CUDA(cudaMalloc(&h->act_stage, act_bytes));
+        h->act_stage_bytes = act_bytes;
+    }
+    DS_CUDA(cudaMemcpyAsync(h->act_stage, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = ds_step(h, h->act_stage, p, io, cuda_stream)) return rc;
+    const size_t zc = (size_t)(h->k + 1) * (h->simplify ? 2 : 5);
+    if (out->pos) DS_CUDA(cudaMemcpyAsync(out->pos, io->pos, A * 2 * rb, cudaMemcpyDeviceToHost, st));
+    if (out->vel) DS_CUDA(cudaMemcpyAsync(out->vel, io->vel, A * 2 * rb, cudaMemcpyDeviceToHost, st));
+    if (out->z) DS_CUDA(cudaMemcpyAsync(out->z, io->z, A * zc * rb, cudaMemcpyDeviceToHost, st));
+    if (out->reward) DS_CUDA(cudaMemcpyAsync(out->reward, io->reward, A * rb, cudaMemcpyDeviceToHost, st));
+    if (out->true_reward)
+        DS_CUDA(cudaMemcpyAsync(out->true_reward, io->true_reward, A * rb, cudaMemcpyDeviceToHost, st));
+    if (out->Ni)
+        DS_CUDA(cudaMemcpyAsync(out->Ni, io->Ni, A * (h->k + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (out->ncoll)
+        DS_CUDA(cudaMemcpyAsync(out->ncoll, io->ncoll, sizeof(int32_t) * h->E, cudaMemcpyDeviceToHost, st));
+    if (out->finished) DS_CUDA(cudaMemcpyAsync(out->finished, io->finished, h->E, cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    return DS_OK;
+}
+
+int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_host_rollout *hr,
+                    void *cuda_stream)
+{
+    if (!h || !hr || !io) return fail(DS_ERR_ARG, "ds_rollout_host: NULL argument");
+    if (int rc = check_params(p)) return rc;
+    if (hr->T < 0) return fail(DS_ERR_ARG, "ds_rollout_host: T < 0");
+    const bool index_mode = hr->actions == nullptr;
+    if (index_mode && (!hr->action_idx || !hr->action_table || hr->n_actions < 1 || hr->n_actions > 256))
+        return fail(DS_ERR_ARG, "ds_rollout_host: give actions, or action_idx + action_table (1..256 rows)");
+    if ((hr->z_tr == nullptr) != (hr->Ni_tr == nullptr))
+        return fail(DS_ERR_ARG, "ds_rollout_host: z_tr and Ni_tr must be given together");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t E = h->E, A = E * h->n, rb = h->real_bytes;
+    const size_t zc = (size_t)(h->k + 1) * (h->simplify ? 2 : 5);
+    // bytes per step of everything that crosses PCIe
+    const size_t in_step = index_mode ? A : A * 2 * rb;
+    size_t out_step = 0;
+    unsigned mask = index_mode ? 1u : 0u;
+    if (hr->pos_tr) { out_step += A * 2 * rb; mask |= 2u; }
+    if (hr->vel_tr) { out_step += A * 2 * rb; mask |= 4u; }
+    if (hr->reward_tr) { out_step += A * rb; mask |= 8u; }
+    if (hr->true_reward_tr) { out_step += A * rb; mask |= 16u; }
+    if (hr->z_tr) { out_step += A * zc * rb + A * (h->k + 1) * 4; mask |= 32u; }
+    if (hr->ncoll_tr) { out_step += E * 4; mask |= 64u; }
+    if (hr->finished_tr) { out_step += E; mask |= 128u; }
+    int chunk = hr->chunk;
+    if (chunk <= 0) {
+        // aim at ~32 MiB per chunk: large enough to reach PCIe bandwidth, small enough to pipeline
+        const size_t per_step = in_step + out_step;
+        chunk = (int)((((size_t)32 << 20) + per_step - 1) / per_step);
+        if (chunk < 1) chunk = 1;
+    }
+    if (chunk > hr->T && hr->T > 0) chunk = hr->T;
+
+    if (!h->s_h2d) DS_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    if (!h->s_d2h) DS_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    if (!h->d_agg) DS_CUDA(cudaMalloc(&h->d_agg, E * 4 * sizeof(double)));
+    if (!h->d_done) DS_CUDA(cudaMalloc(&h->d_done, E));
+    if (index_mode) {
+        if (!h->d_atable) DS_CUDA(cudaMalloc(&h->d_atable, 256 * 2 * sizeof(double)));
+        DS_CUDA(cudaMemcpyAsync(h->d_atable, hr->action_table, (size_t)hr->n_actions * 2 * rb,
+                                cudaMemcpyHostToDevice, st));
+    }
+    if (h->slot_chunk < chunk || h->slot_mask != mask) {
+        DS_CUDA(cudaDeviceSynchronize());
+        free_slots(h);
+        for (auto &s : h->slot) {
+            const size_t c = chunk;
+            if (index_mode) DS_CUDA(cudaMalloc(&s.aidx, c * A)); else DS_CUDA(cudaMalloc(&s.act, c * A * 2 * rb));
+            if (hr->pos_tr) DS_CUDA(cudaMalloc(&s.pos, c * A * 2 * rb));
+            if (hr->vel_tr) DS_CUDA(cudaMalloc(&s.vel, c * A * 2 * rb));
+            if (hr->reward_tr) DS_CUDA(cudaMalloc(&s.r, c * A * rb));
+            if (hr->true_reward_tr) DS_CUDA(cudaMalloc(&s.tr, c * A * rb));
+            if (hr->z_tr) {
+                DS_CUDA(cudaMalloc(&s.z, c * A * zc * rb));
+                DS_CUDA(cudaMalloc(&s.Ni, c * A * (h->k + 1) * 4));
+            }
+            if (hr->ncoll_tr) DS_CUDA(cudaMalloc(&s.ncoll, c * E * 4));
+            if (hr->finished_tr) DS_CUDA(cudaMalloc(&s.fin, c * E));
+            DS_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+            DS_CUDA(cudaEventCreateWithFlags(&s.kernel_done, cudaEventDisableTiming));
+            DS_CUDA(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
+        }
+        h->slot_chunk = chunk; h->slot_mask = mask;
+    }
+    DS_CUDA(cudaMemsetAsync(h->d_agg, 0, E * 4 * sizeof(double), st));
+    DS_CUDA(cudaMemsetAsync(h->d_done, 0, E, st));
+    // the copy streams must not start before the caller's stream reaches this point
+    cudaEvent_t &start_ev = h->slot[0].d2h_done;   // reuse: recorded before any D2H of this call
+    DS_CUDA(cudaEventRecord(start_ev, st));
+    DS_CUDA(cudaStreamWaitEvent(h->s_h2d, start_ev, 0));
+    DS_CUDA(cudaStreamWaitEvent(h->s_d2h, start_ev, 0));
+    DS_CUDA(cudaEventRecord(h->slot[1].d2h_done, st));
+
+    int ci = 0;
+    for (int t0 = 0; t0 < hr->T; t0 += chunk, ++ci) {
+        const int tc = (hr->T - t0 < chunk) ? hr->T - t0 : chunk;
+        ds_handle::Slot &s = h->slot[ci & 1];
+        const size_t t0s = t0, tcs = tc;
+        // H2D: the slot's action buffer is free once the kernel of chunk ci-2 has run
+        if (ci >= 2) DS_CUDA(cudaStreamWaitEvent(h->s_h2d, s.kernel_done, 0));
+        if (index_mode)
+            DS_CUDA(cudaMemcpyAsync(s.aidx, hr->action_idx + t0s * A, tcs * A, cudaMemcpyHostToDevice, h->s_h2d));
+        else
+            DS_CUDA(cudaMemcpyAsync(s.act, (const char *)hr->actions + t0s * A * 2 * rb, tcs * A * 2 * rb,
+                                    cudaMemcpyHostToDevice, h->s_h2d));
+        DS_CUDA(cudaEventRecord(s.h2d_done, h->s_h2d));
+        // kernel: needs the actions, and the slot's output buffers drained (chunk ci-2's D2H)
+        DS_CUDA(cudaStreamWaitEvent(st, s.h2d_done, 0));
+        DS_CUDA(cudaStreamWaitEvent(st, s.d2h_done, 0));
+        ds_rollout_io ro;
+        std::memset(&ro, 0, sizeof ro);
+        ro.T = tc; ro.n_actions = hr->n_actions;
+        ro.actions = index_mode ? nullptr : s.act;
+        ro.action_idx = s.aidx; ro.action_table = h->d_atable;
+        ro.pos_tr = s.pos; ro.vel_tr = s.vel; ro.reward_tr = s.r; ro.true_reward_tr = s.tr;
+        ro.z_tr = s.z; ro.Ni_tr = s.Ni; ro.ncoll_tr = s.ncoll; ro.finished_tr = s.fin;
+        ro.agg = h->d_agg; ro.done = h->d_done;
+        if (int rc = ds_rollout(h, p, io, &ro, cuda_stream)) return rc;
+        DS_CUDA(cudaEventRecord(s.kernel_done, st));
+        // D2H
+        DS_CUDA(cudaStreamWaitEvent(h->s_d2h, s.kernel_done, 0));
+        cudaStream_t d = h->s_d2h;
+        if (hr->pos_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->pos_tr + t0s * A * 2 * rb, s.pos, tcs * A * 2 * rb, cudaMemcpyDeviceToHost, d));
+        if (hr->vel_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->vel_tr + t0s * A * 2 * rb, s.vel, tcs * A * 2 * rb, cudaMemcpyDeviceToHost, d));
+        if (hr->reward_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->reward_tr + t0s * A * rb, s.r, tcs * A * rb, cudaMemcpyDeviceToHost, d));
+        if (hr->true_reward_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->true_reward_tr + t0s * A * rb, s.tr, tcs * A * rb, cudaMemcpyDeviceToHost, d));
+        if (hr->z_tr) {
+            DS_CUDA(cudaMemcpyAsync((char *)hr->z_tr + t0s * A * zc * rb, s.z, tcs * A * zc * rb, cudaMemcpyDeviceToHost, d));
+            DS_CUDA(cudaMemcpyAsync(hr->Ni_tr + t0s * A * (h->k + 1), s.Ni, tcs * A * (h->k + 1) * 4, cudaMemcpyDeviceToHost, d));
+        }
+        if (hr->ncoll_tr) DS_CUDA(cudaMemcpyAsync(hr->ncoll_tr + t0s * E, s.ncoll, tcs * E * 4, cudaMemcpyDeviceToHost, d));
+        if (hr->finished_tr) DS_CUDA(cudaMemcpyAsync(hr->finished_tr + t0s * E, s.fin, tcs * E, cudaMemcpyDeviceToHost, d));
+        DS_CUDA(cudaEventRecord(s.d2h_done, d));
+    }
+    if (hr->agg)
+        DS_CUDA(cudaMemcpyAsync(hr->agg, h->d_agg, E * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    DS_CUDA(cudaStreamSynchronize(h->s_d2h));
+    DS_CUDA(cudaStreamSynchronize(h->s_h2d));
+    return DS_OK;
+}
+
+}  // extern "C"

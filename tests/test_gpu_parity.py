@@ -1,0 +1,316 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes ->
+libdronestep.so), against (a) the golden vectors recorded from the unmodified
+reference and (b) the C oracle on seeded random inputs.
+
+Tolerances: BASELINE.json's contract is |delta| <= 1e-5 on float state/reward and
+bit-exact integer collision counts.  The float64 instantiation is asserted at
+1e-9 (and positions bit-exact); the float32 throughput mode has its own stated
+relative tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CONTRACT_TOL, FP64_TOL, assert_close, compare_obs, golden_names, load_golden
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(g, E, dtype=torch.float64, log_mode=0):
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    deltas_in = g["deltas_in"] if g["deltas_in"].size else None
+    env = BatchedDrones(E, g["n"], list(g["grid"]), "O", g["k"], deltas_in, bool(g["simplify"]),
+                        dtype=dtype, seed=0, warn=False)
+    env.collision_weight = g["collision_weight"]
+    env.log_mode = log_mode
+    # host-side setup must reproduce the reference's constructor outputs bit for bit
+    assert np.array_equal(env.end_points, g["end_points"])
+    assert np.array_equal(env.d_safety, g["d_safety"])
+    assert np.array_equal(np.asarray(env.deltas, np.float64), g["deltas"])
+    return env
+
+
+@pytest.mark.parametrize("log_mode", [0, 1])
+@pytest.mark.parametrize("name", golden_names())
+def test_step_vs_reference_golden(name, log_mode):
+    """Every recorded reference step, teacher-forced, as one batch of E = T environments."""
+    g = load_golden(name)
+    T = len(g["ncoll"])
+    env = _mk(g, T, log_mode=log_mode)
+    env.set_state(g["state_in"], g["t_in"])
+    act = torch.as_tensor(g["actions"], device=env.device)
+    (pos, vel), z, r, ncoll, fin, true_r = env.step(act)
+    torch.cuda.synchronize()
+    assert_close(pos.cpu().numpy(), g["state"][:, :, 0:2], 0.0, "pos (bit-exact)")
+    assert_close(vel.cpu().numpy(), g["state"][:, :, 2:4], 0.0, "vel (bit-exact)")
+    assert_close(r.cpu().numpy(), g["r"], FP64_TOL, "reward")
+    assert_close(true_r.cpu().numpy(), g["true_r"], FP64_TOL, "true reward")
+    assert np.array_equal(ncoll.cpu().numpy().astype(np.int64), g["ncoll"]), "collision counts"
+    assert np.array_equal(fin.cpu().numpy(), g["finished"]), "finished"
+    assert np.array_equal(env.internal_t.cpu().numpy(), g["t_in"] + 1)
+    compare_obs(z.cpu().numpy(), env.Ni.cpu().numpy(), g["z"], g["Ni"], g["tie"], FP64_TOL, name)
+
+
+@pytest.mark.parametrize("name", ["policy_n5_seed0", "policy_n5_seed1", "free_n10_g5_d1.0",
+                                  "free_n8_g5_d1.0_k3_cw0.5", "free_n5_g5_dNone_full"])
+def test_dropin_class_lockstep(name):
+    """The reference-facing class `drone_env.drones`, free-running a whole recorded episode
+    (BASELINE config 1 for the policy_* fixtures) with only the action stream shared."""
+    import random
+    import drone_env
+    g = load_golden(name)
+    deltas_in = g["deltas_in"] if g["deltas_in"].size else None
+    random.seed(0)
+    env = drone_env.drones(n_agents=g["n"], n_obstacles=0, grid=[float(x) for x in g["grid"]],
+                           end_formation="O", k_closest=g["k"], deltas=deltas_in,
+                           simplify_zstate=bool(g["simplify"]))
+    env.collision_weight = g["collision_weight"]      # mutated after construction (train_problem.py:31)
+    assert np.array_equal(env.end_points, g["end_points"]) and np.array_equal(env.d_safety, g["d_safety"])
+    assert env.local_state_space == (2 if g["simplify"] else 5) * (g["k"] + 1)
+    env.state[:, :] = g["state0"]                     # inject the reference's start state
+    _, _, z0, Ni0, _ = env.rewards(env.state, env.end_points, env.n_agents, env.d_safety, env.deltas)
+    pad0 = np.full((g["n"], g["k"] + 1), -1)
+    for i, l in enumerate(Ni0):
+        pad0[i, :len(l)] = l
+    compare_obs(np.array(z0), pad0, g["z0"], g["Ni0"], g["tie0"], FP64_TOL, name + " init")
+    ret = coll = 0
+    for t in range(len(g["ncoll"])):
+        state, z, r, ncoll, fin, true_r = env.step([g["actions"][t][i] for i in range(g["n"])])
+        assert state is env.state                                  # aliasing contract (drone_env.py:258)
+        assert isinstance(fin, bool) and isinstance(ncoll, np.integer)
+        assert_close(state, g["state"][t], 0.0, f"state t={t} (bit-exact)")
+        assert_close(r, g["r"][t], FP64_TOL, f"r t={t}")
+        assert_close(true_r, g["true_r"][t], FP64_TOL, f"true_r t={t}")
+        assert int(ncoll) == int(g["ncoll"][t]) and fin == bool(g["finished"][t])
+        pad = np.full((g["n"], g["k"] + 1), -1)
+        for i, l in enumerate(env.Ni):
+            assert l[0] == i
+            pad[i, :len(l)] = l
+        compare_obs(np.array(z), pad, g["z"][t], g["Ni"][t], g["tie"][t], FP64_TOL, f"{name} t={t}")
+        ret += float(np.mean(r)); coll += int(ncoll)
+    assert abs(ret - g["r"].mean(1).sum()) < 1e-9 and coll == int(g["ncoll"].sum())
+    env.reset(renew_obstacles=False)
+    assert env.internal_t == 0 and np.all(env.state[:, 2:4] == 0)
+
+
+def _random_case(n, E, k, simplify, grid, delta, seed, box=None, hetero=False):
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    rng = np.random.default_rng(seed)
+    deltas = (rng.uniform(0.2, delta, n) if hetero else np.ones(n) * delta)
+    env = BatchedDrones(E, n, grid, "O", k, deltas, simplify, seed=seed, warn=False)
+    box = box or grid[0]
+    pos = rng.uniform(0, box, (E, n, 2))
+    vel = rng.standard_normal((E, n, 2))
+    t = rng.integers(0, 205, E).astype(np.int32)
+    act = rng.uniform(-1, 1, (E, n, 2))
+    state = np.concatenate([pos, vel, np.full((E, n, 1), 0.1)], 2)
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, k, simplify,
+                             c_oracle.default_params(env.collision_weight), nthreads=8)
+    orc.set_state(pos, vel, t)
+    env.set_state(state, t)
+    return env, orc, act
+
+
+CASES = [  # n, E, k, simplify, grid, delta, box, hetero
+    (5, 777, 2, True, [5, 5], 1.0, 2.0, False),
+    (10, 512, 2, True, [5, 5], 1.0, 3.0, False),
+    (10, 300, 2, False, [5, 5], 1.0, 2.0, True),
+    (7, 301, 0, True, [5, 5], 1.0, 2.0, False),
+    (9, 257, 1, False, [5, 5], 1.0, 2.0, False),
+    (12, 129, 4, True, [8, 8], 1.5, 3.0, True),
+    (20, 65, 6, False, [16, 16], 2.0, 5.0, False),    # dynamic-k kernel
+    (32, 200, 2, True, [32, 32], 2.5, 8.0, False),
+    (33, 100, 2, True, [32, 32], 2.5, 8.0, False),    # first CTA-group size
+    (64, 50, 3, False, [32, 32], 1.0, 6.0, True),
+    (128, 24, 2, True, [64, 64], 1.0, 12.0, False),
+    (300, 5, 2, True, [128, 128], 1.0, 20.0, False),  # > 256 threads per environment
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c[0]}_E{c[1]}_k{c[2]}_{'s' if c[3] else 'f'}")
+def test_step_vs_oracle_random(case):
+    """Seeded dense random states (collisions guaranteed) against the C oracle."""
+    n, E, k, simplify, grid, delta, box, hetero = case
+    env, orc, act = _random_case(n, E, k, simplify, grid, delta, 1000 + n, box, hetero)
+    ref = orc.step(act)
+    (pos, vel), z, r, ncoll, fin, true_r = env.step(torch.as_tensor(act, device=env.device))
+    torch.cuda.synchronize()
+    assert ref.ncoll.sum() > 0, "test must exercise collisions"
+    assert_close(pos.cpu().numpy(), ref.pos, 0.0, "pos")
+    assert_close(r.cpu().numpy(), ref.r, FP64_TOL, "reward")
+    assert_close(true_r.cpu().numpy(), ref.true_r, FP64_TOL, "true reward")
+    assert np.array_equal(ncoll.cpu().numpy(), ref.ncoll)
+    assert np.array_equal(fin.cpu().numpy(), ref.finished)
+    compare_obs(z.cpu().numpy(), env.Ni.cpu().numpy(), ref.z, ref.Ni, ref.tie, FP64_TOL, "obs")
+    # observe(): same evaluation without integrating, t/finished untouched
+    t_before = env.internal_t.clone()
+    env.observe()
+    torch.cuda.synchronize()
+    assert torch.equal(env.internal_t, t_before)
+    assert_close(env.rewards.cpu().numpy(), ref.r, FP64_TOL, "observe reward")
+
+
+@pytest.mark.parametrize("n,E,grid,delta", [(5, 96, [5, 5], 1.0), (10, 64, [5, 5], 1.0),
+                                            (32, 16, [32, 32], 2.5), (40, 9, [32, 32], 2.5)])
+def test_rollout_vs_oracle_and_stepping(n, E, grid, delta):
+    """ds_rollout (T fused steps) == T x ds_step bit for bit, and == the oracle's episode loop,
+    including early termination, frozen finished envs and the episode aggregates."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    T = 60
+    rng = np.random.default_rng(n)
+    tab = np.stack([np.cos(np.arange(16) / 16 * 2 * np.pi), np.sin(np.arange(16) / 16 * 2 * np.pi)], 1)
+    idx = rng.integers(0, 16, (T, E, n)).astype(np.uint8)
+    act = tab[idx]
+    envA = BatchedDrones(E, n, grid, "O", 2, np.ones(n) * delta, True, seed=5, warn=False)
+    start = envA.pos.cpu().numpy().copy()
+    t0 = rng.integers(150, 199, E).astype(np.int32)      # some envs hit the 200-step limit inside T
+    state = np.concatenate([start, np.zeros((E, n, 2)), np.full((E, n, 1), 0.1)], 2)
+    envA.set_state(state, t0)
+    envB = BatchedDrones(E, n, grid, "O", 2, np.ones(n) * delta, True, seed=5, warn=False)
+    envB.set_state(state, t0)
+    envC = BatchedDrones(E, n, grid, "O", 2, np.ones(n) * delta, True, seed=5, warn=False)
+    envC.set_state(state, t0)
+    orc = c_oracle.OracleEnv(E, n, envA.end_points, envA.d_safety, envA.deltas, None, 2, True,
+                             c_oracle.default_params(envA.collision_weight))
+    orc.set_state(start, None, t0)
+    ref = orc.rollout(act)
+    rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
+    out = envA.rollout(actions=torch.as_tensor(act, device=envA.device), record=rec)
+    outC = envC.rollout(action_idx=torch.as_tensor(idx, device=envC.device), action_table=tab, record=rec)
+    torch.cuda.synchronize()
+    fin_tr = out["finished"].cpu().numpy()
+    assert np.array_equal(fin_tr, ref["finished"])
+    live = fin_tr != 2
+    assert (fin_tr == 2).any() and (fin_tr == 1).any()
+    assert_close(out["reward"].cpu().numpy()[live], ref["r"][live], FP64_TOL, "rollout r")
+    assert_close(out["true_reward"].cpu().numpy()[live], ref["true_r"][live], FP64_TOL, "rollout true r")
+    assert np.array_equal(out["ncoll"].cpu().numpy()[live], ref["ncoll"][live])
+    assert_close(out["agg"].cpu().numpy(), ref["agg"], 1e-9, "episode aggregates")
+    assert np.array_equal(out["done"].cpu().numpy(), ref["done"])
+    assert_close(envA.pos.cpu().numpy(), ref["pos"], 0.0, "final pos")
+    assert np.array_equal(envA.internal_t.cpu().numpy(), ref["t"])
+    lv_t = torch.as_tensor(live, device=envA.device)   # index mode == real-valued mode, bit for bit
+    for key in ("pos", "reward", "true_reward", "z", "Ni", "ncoll"):
+        assert torch.equal(out[key][lv_t], outC[key][lv_t]), key
+    # stepping envB one launch at a time reproduces the fused trajectory exactly
+    done = np.zeros(E, bool)
+    for t in range(T):
+        before = (envB.pos.clone(), envB.vel.clone(), envB.internal_t.clone())
+        envB.step(torch.as_tensor(act[t], device=envB.device))
+        torch.cuda.synchronize()
+        # freeze finished environments like the rollout does
+        d = torch.as_tensor(done, device=envB.device)
+        envB.pos[d] = before[0][d]; envB.vel[d] = before[1][d]; envB.internal_t[d] = before[2][d]
+        lv = ~done
+        assert torch.equal(envB.rewards[torch.as_tensor(lv, device=envB.device)],
+                           out["reward"][t][torch.as_tensor(lv, device=envB.device)])
+        assert torch.equal(envB.z_states[torch.as_tensor(lv, device=envB.device)],
+                           out["z"][t][torch.as_tensor(lv, device=envB.device)])
+        done |= envB.finished.cpu().numpy().astype(bool) & lv
+    assert torch.equal(envB.pos, envA.pos)
+    # device-side reduction of the aggregates (the vector a rank all-reduces)
+    s = envA.episode_aggregates().cpu().numpy()
+    assert_close(s[:4], ref["agg"].sum(0), 1e-6, "reduced aggregates")
+    assert s[4] == E
+
+
+def test_host_entries_match_device_entries():
+    """ds_step_host / ds_rollout_host (host buffers, copies inside) == device-pointer entries."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    n, E, T = 10, 200, 37
+    rng = np.random.default_rng(3)
+    act = rng.uniform(-1, 1, (T, E, n, 2))
+    a = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    b = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    assert torch.equal(a.pos, b.pos)
+    o = b.step_host(act[0])
+    a.step(torch.as_tensor(act[0], device=a.device))
+    torch.cuda.synchronize()
+    assert np.array_equal(o["pos"], a.pos.cpu().numpy()) and np.array_equal(o["r"], a.rewards.cpu().numpy())
+    assert np.array_equal(o["z"], a.z_states.cpu().numpy()) and np.array_equal(o["Ni"], a.Ni.cpu().numpy())
+    assert np.array_equal(o["nc"], a.n_collisions.cpu().numpy())
+    rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
+    da = a.rollout(actions=torch.as_tensor(act[1:], device=a.device), record=rec)
+    for chunk in (0, 5, 36, 100):
+        b2 = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+        b2.step_host(act[0])
+        hb = b2.rollout_host(actions=act[1:], record=rec, chunk=chunk)
+        torch.cuda.synchronize()
+        for key in ("pos", "vel", "reward", "true_reward", "z", "Ni", "ncoll", "finished"):
+            assert torch.equal(hb[key], da[key].cpu()), f"{key} chunk={chunk}"
+        assert torch.equal(hb["agg"], da["agg"].cpu())
+
+
+@pytest.mark.parametrize("n,grid,delta", [(10, [5, 5], 1.0), (32, [32, 32], 2.5)])
+def test_float32_throughput_mode(n, grid, delta):
+    """float32 instantiation, fed the oracle's state: stated tolerance is RELATIVE,
+    |dr| <= 2e-6 * max(1, |r|) per step on collision-free states (fp32 cannot meet 1e-5 absolute
+    on |r| ~ 100), collision counts compared where no pair sits within
+    1e-5 of contact."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    E = 256
+    rng = np.random.default_rng(11)
+    env = BatchedDrones(E, n, grid, "O", 2, np.ones(n) * delta, True, dtype=torch.float32, seed=1, warn=False)
+    pos = env.pos.cpu().numpy().astype(np.float64)      # lattice start: exactly representable path
+    act = rng.uniform(-1, 1, (E, n, 2)).astype(np.float32)
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, 2, True,
+                             c_oracle.default_params(env.collision_weight))
+    orc.set_state(pos)
+    ref = orc.step(act.astype(np.float64))
+    (p32, _), z, r, ncoll, fin, tr = env.step(torch.as_tensor(act, device=env.device))
+    torch.cuda.synchronize()
+    assert np.abs(p32.cpu().numpy() - ref.pos).max() < 1e-5
+    err = np.abs(r.cpu().numpy() - ref.r) / np.maximum(1.0, np.abs(ref.r))
+    assert err.max() < 2e-6, err.max()
+    assert np.array_equal(ncoll.cpu().numpy(), ref.ncoll)
+
+
+def test_full_size_properties():
+    """BASELINE config 3 (n = 10, E = 4096) at full size: size-independent invariants."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    n, E = 10, 4096
+    rng = np.random.default_rng(0)
+    env = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=0, warn=False)
+    p0 = env.pos.cpu().numpy()
+    # reset: distinct lattice nodes, no initial overlap, zero velocity
+    d = np.linalg.norm(p0[:, :, None] - p0[:, None, :], axis=-1) + np.eye(n) * 9
+    assert d.min() >= 0.22 - 1e-12 and int(env.n_collisions.sum()) == 0
+    act = rng.uniform(-1, 1, (E, n, 2))
+    perm = rng.permutation(E)
+    env2 = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=0, warn=False, start_positions=p0[perm])
+    for _ in range(3):
+        env.step(torch.as_tensor(act, device=env.device))
+        env2.step(torch.as_tensor(act[perm], device=env.device))
+    torch.cuda.synchronize()
+    # environments are independent: permuting the batch permutes the outputs bit for bit
+    pt = torch.as_tensor(perm, device=env.device)
+    assert torch.equal(env.rewards[pt], env2.rewards) and torch.equal(env.z_states[pt], env2.z_states)
+    assert torch.equal(env.n_collisions[pt], env2.n_collisions)
+    r, tr = env.rewards.cpu().numpy(), env.true_rewards.cpu().numpy()
+    assert (r <= 0).all() and (tr <= r + 1e-12).all()       # barrier terms are >= 0; global has more of them
+    assert (env.n_collisions.cpu().numpy() % 2 == 0).all()  # ordered pairs, uniform radius (README.md:46)
+    Ni = env.Ni.cpu().numpy()
+    assert (Ni[:, :, 0] == np.arange(n)[None]).all() and (Ni >= -1).all() and (Ni < n).all()
+    # checksum of checksums against the oracle on the same inputs
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, 2, True,
+                             c_oracle.default_params(env.collision_weight), nthreads=8)
+    orc.set_state(p0)
+    for _ in range(3):
+        ref = orc.step(act)
+    assert_close(r, ref.r, FP64_TOL, "full-size reward")
+    assert int(env.n_collisions.sum()) == int(ref.ncoll.sum())
+
+
+def test_error_behaviour():
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, DroneStepError
+    with pytest.raises(DroneStepError):
+        BatchedDrones(4, 3, [5, 5], "O", 3, None, True, warn=False)        # k >= n
+    with pytest.raises(ValueError):
+        BatchedDrones(4, 3, [5, 5], "X", 2, None, True, warn=False)        # unknown formation
+    env = BatchedDrones(4, 3, [5, 5], "O", 2, None, True, warn=False)
+    with pytest.raises(TypeError):
+        env.step(np.zeros((4, 3, 2)))
+    env.log_mode = 7
+    with pytest.raises(DroneStepError):
+        env.observe()
