@@ -100,21 +100,26 @@ def sample_start_batched(n_envs: int, n_agents: int, grid, rng: np.random.Genera
     L = d0 * d1
     if n_agents > L:
         raise ValueError("Sample larger than population or is negative")   # as random.sample
-    if L <= 4096:
-        keys = rng.random((n_envs, L))
-        picks = np.argpartition(keys, n_agents - 1, axis=1)[:, :n_agents]
-        # argpartition leaves the first n in arbitrary order; shuffle for an unbiased order
-        picks = rng.permuted(picks, axis=1)
-    else:
-        picks = rng.integers(0, L, size=(n_envs, n_agents))
-        for _ in range(64):                                   # rejection on the rare duplicates
-            srt = np.sort(picks, axis=1)
-            bad = (srt[:, 1:] == srt[:, :-1]).any(1)
-            if not bad.any():
-                break
-            picks[bad] = rng.integers(0, L, size=(int(bad.sum()), n_agents))
+    picks = np.empty((n_envs, n_agents), np.int64)
+    block = max(1, (1 << 24) // max(L, 1))                    # bound the key matrix to ~128 MB
+    for lo in range(0, n_envs, block):
+        m = min(block, n_envs - lo)
+        if L <= 4096:
+            keys = rng.random((m, L))
+            sel = np.argpartition(keys, n_agents - 1, axis=1)[:, :n_agents]
+            # argpartition leaves the first n in arbitrary order; shuffle for an unbiased order
+            picks[lo:lo + m] = rng.permuted(sel, axis=1)
         else:
-            raise RuntimeError("could not draw distinct lattice nodes")
+            sel = rng.integers(0, L, size=(m, n_agents))
+            for _ in range(64):                               # rejection on the rare duplicates
+                srt = np.sort(sel, axis=1)
+                bad = (srt[:, 1:] == srt[:, :-1]).any(1)
+                if not bad.any():
+                    break
+                sel[bad] = rng.integers(0, L, size=(int(bad.sum()), n_agents))
+            else:
+                raise RuntimeError("could not draw distinct lattice nodes")
+            picks[lo:lo + m] = sel
     return lattice_coords(picks, grid)
 
 
