@@ -39,7 +39,7 @@ WORKLOADS = {   # BASELINE.json configs[1..4]
     "config4": dict(n=32, E=8192, grid=[32, 32], delta=2.5),
     "config5": dict(n=128, E=1024, grid=[64, 64], delta=1.0),
     # HBM-resident point for the ncu capture (working set per step >> L2)
-    "hbm": dict(n=10, E=1 << 20, grid=[5, 5], delta=1.0),
+    "hbm": dict(n=10, E=1 << 20, grid=[5, 5], delta=1.0, episode=20),
 }
 EPISODE = 200
 N_ACTIONS = 16
@@ -65,53 +65,64 @@ def bytes_per_agent_step(rb, n, k=K_CLOSEST, cols=2, mode="rollout"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    (nvidia-smi's own start-up time is longer than a short timed region)."""
+    HW_SLOWDOWN, SW_POWER_CAP, SW_THERMAL, HW_THERMAL = 0x8, 0x4, 0x20, 0x40
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.index, self.rows, self.thread, self.stop_flag, self.h = index, [], None, False, None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # torch device ordinals follow CUDA_VISIBLE_DEVICES; NVML sees every device of the box
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except ValueError:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.h = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.h is None:
+            return
+        self.stop_flag = False
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            f = [x.strip() for x in row.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None or self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        bits = 0
+        for _, rs in self.rows:
+            bits |= int(rs)
+        reasons = [name for name, bit in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                                          ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP))
+                   if bits & bit]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm),
+                "samples": len(sm), "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------- CPU legs
@@ -223,7 +234,7 @@ def run_ours(args, wl):
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     rb = 8 if args.dtype == "f64" else 4
     K, W = args.steps, args.warmup
-    T = min(args.episode_steps or EPISODE, K)
+    T = min(args.episode_steps or wl.get("episode", EPISODE), K)
     rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
 
     env = BatchedDrones(E, n, grid, "O", K_CLOSEST, np.ones(n) * wl["delta"], True, dtype=dtype,
@@ -233,8 +244,10 @@ def run_ours(args, wl):
     tab = formation.unit_action_table(N_ACTIONS)
     # synthetic inputs resident in HBM before the timed region: action stream + episode starts
     n_ep_bufs = 2
-    idx = torch.as_tensor(rng.integers(0, N_ACTIONS, (n_ep_bufs, T, E, n)), device=dev)
-    actions = torch.as_tensor(tab, dtype=dtype, device=dev)[idx]          # [bufs,T,E,n,2] Real
+    gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
+    idx = torch.randint(0, N_ACTIONS, (n_ep_bufs, T, E, n), device=dev, generator=gen, dtype=torch.uint8)
+    actions = torch.as_tensor(tab, dtype=dtype, device=dev)[idx.long()]   # [bufs,T,E,n,2] Real
+    del idx
     starts = torch.as_tensor(formation.sample_start_batched(n_ep_bufs * E, n, grid, rng)
                              .reshape(n_ep_bufs, E, n, 2), dtype=dtype, device=dev)
     out = {}
@@ -368,8 +381,8 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=600)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])

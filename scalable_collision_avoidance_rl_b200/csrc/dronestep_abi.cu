@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -35,12 +36,16 @@ int fail(int code, const std::string &msg)
 struct ds_handle {
     int E, n, k, simplify, real_bytes, device;
     int sm_count;
-    // launch geometry
-    int mode;                 // 0 warp groups, 1 CTA <= 256 threads, 2 CTA <= 1024 threads
-    int epg, threads, blocks;
-    size_t smem;
-    // device constants (Real typed)
-    void *d_xF, *d_ds, *d_delta, *d_radius, *d_logds;
+    // launch geometry: a CTA owns G whole environments (x TC time slices in a rollout)
+    int nt;                   // thread cap of the kernel instantiation: 256 (n <= 256) or 1024
+    int step_G, step_threads, step_blocks;
+    size_t step_smem;
+    int ro_G, ro_TC, ro_threads, ro_blocks;
+    size_t ro_smem;
+    size_t smem_optin;
+    // device constants (Real typed unless noted)
+    void *d_xF, *d_ds, *d_delta, *d_radius, *d_logds, *d_thr2;
+    int *d_clipcnt;
     std::vector<double> h_radius;
     // staging for the host-buffer entries
     void *act_stage;
@@ -64,7 +69,8 @@ template <typename Real>
 int upload_consts(ds_handle *h, const ds_config *cfg)
 {
     const int n = h->n;
-    std::vector<Real> xF(2 * n), dsv(n), dl(n), rd(n), lg(n);
+    std::vector<Real> xF(2 * n), dsv(n), dl(n), rd(n), lg(n), thr2(n);
+    std::vector<int> clipcnt(n);
     for (int i = 0; i < n; ++i) {
         xF[2 * i] = (Real)cfg->end_points[2 * i];
         xF[2 * i + 1] = (Real)cfg->end_points[2 * i + 1];
@@ -73,39 +79,86 @@ int upload_consts(ds_handle *h, const ds_config *cfg)
         rd[i] = (Real)cfg->radius[i];
         lg[i] = (Real)std::log(std::fabs(cfg->d_safety[i]));
     }
+    // Fast-reject threshold of eval_row's pass 1.  A pair (i, j) is clipped to d_safety[i]
+    // (drone_env.py:318) when  fl(fl(dist - l_i) - l_j) >= d_safety[i];  with
+    // D = d_safety[i] + l_i + max_j l_j this is implied by  dist^2 >= (D (1 + m) + m)^2 (1 + m)
+    // for a margin m far above the rounding error of the Real chain (pairs inside the margin
+    // simply take the exact path).  No fast path when d_safety[i] == 0 (the d == 0 -> -1e-6
+    // rule, :319-320, then turns clipped pairs into collisions), when D is not safely
+    // positive, or for non-finite constants.
+    Real rmax = 0;
+    for (int i = 0; i < n; ++i) rmax = (rd[i] > rmax) ? rd[i] : rmax;
+    const double m = sizeof(Real) == 8 ? 1e-12 : 1e-5;
+    for (int i = 0; i < n; ++i) {
+        const double D = (double)dsv[i] + (double)rd[i] + (double)rmax;
+        double t2 = INFINITY;
+        if (dsv[i] != (Real)0 && std::isfinite(D) && D > 1e-6) {
+            const double thr = D * (1 + m) + m;
+            t2 = thr * thr * (1 + m);
+        }
+        thr2[i] = (Real)t2;
+        if (!(thr2[i] >= t2)) thr2[i] = (Real)INFINITY;   // never round the threshold down
+        int cc = 0;
+        for (int j = 0; j < n; ++j)
+            if (j != i && dsv[i] <= dl[j]) ++cc;            // :328 for a clipped pair, evaluated in Real
+        clipcnt[i] = cc;
+    }
     DS_CUDA(cudaMalloc(&h->d_xF, sizeof(Real) * 2 * n));
     DS_CUDA(cudaMalloc(&h->d_ds, sizeof(Real) * n));
     DS_CUDA(cudaMalloc(&h->d_delta, sizeof(Real) * n));
     DS_CUDA(cudaMalloc(&h->d_radius, sizeof(Real) * n));
     DS_CUDA(cudaMalloc(&h->d_logds, sizeof(Real) * n));
+    DS_CUDA(cudaMalloc(&h->d_thr2, sizeof(Real) * n));
+    DS_CUDA(cudaMalloc((void **)&h->d_clipcnt, sizeof(int) * n));
     DS_CUDA(cudaMemcpy(h->d_xF, xF.data(), sizeof(Real) * 2 * n, cudaMemcpyHostToDevice));
     DS_CUDA(cudaMemcpy(h->d_ds, dsv.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
     DS_CUDA(cudaMemcpy(h->d_delta, dl.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
     DS_CUDA(cudaMemcpy(h->d_radius, rd.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
     DS_CUDA(cudaMemcpy(h->d_logds, lg.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(h->d_thr2, thr2.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
+    DS_CUDA(cudaMemcpy(h->d_clipcnt, clipcnt.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     return DS_OK;
 }
 
+int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+size_t cta_smem(const ds_handle *h, int G, int TC)
+{
+    return h->real_bytes == 8 ? ds::CtaSmem<double>::bytes(h->n, G, TC) : ds::CtaSmem<float>::bytes(h->n, G, TC);
+}
+
+// One item (agent of one environment at one time slice) per thread.  step: CTA = G whole
+// environments.  rollout: CTA = G environments x TC concurrent time slices; (G, TC) is the pair
+// that fills the most threads of the CTA with TC <= 8, larger TC on ties.  DS_PLAN_G / DS_PLAN_TC
+// override the rollout plan (tuning experiments).
 void plan_launch(ds_handle *h)
 {
-    const int n = h->n;
-    h->mode = n <= 32 ? 0 : (n <= 256 ? 1 : 2);
-    if (h->mode == 0) {
-        h->epg = 32 / n;                       // whole environments per warp
-        h->threads = 128;                      // 4 warps (groups) per CTA
-        const long long groups = ((long long)h->E + h->epg - 1) / h->epg;
-        h->blocks = (int)((groups + 3) / 4);
-    } else {
-        h->epg = 256 / n > 0 ? 256 / n : 1;    // whole environments per CTA
-        h->threads = ((h->epg * n + 31) / 32) * 32;
-        h->blocks = (int)(((long long)h->E + h->epg - 1) / h->epg);
+    const int n = h->n, E = h->E;
+    h->nt = n <= 256 ? 256 : 1024;
+    const int cap = n <= 256 ? 256 : ((n + 31) / 32) * 32;
+    auto clampG = [&](int G) { G = G < 1 ? 1 : G; return G > E ? E : G; };
+    h->step_G = clampG(cap / n);
+    h->step_threads = ((h->step_G * n + 31) / 32) * 32;
+    h->step_blocks = (int)(((long long)E + h->step_G - 1) / h->step_G);
+    h->step_smem = cta_smem(h, h->step_G, 1);
+    int bestG = 1, bestTC = 1, best = 0;
+    const int tcmax = env_int("DS_PLAN_TCMAX", 8);
+    for (int TC = 1; TC <= tcmax; ++TC) {
+        const int G = clampG(cap / (n * TC));
+        const int items = G * n * TC;
+        if (items > cap && TC > 1) continue;
+        if (items >= best) { best = items; bestG = G; bestTC = TC; }
     }
-    const int gpb = h->mode == 0 ? 4 : 1;
-    if (h->real_bytes == 8)
-        h->smem = ds::GroupSmem<double>::const_bytes(n) + ds::GroupSmem<double>::group_bytes(h->epg, n) * gpb;
-    else
-        h->smem = ds::GroupSmem<float>::const_bytes(n) + ds::GroupSmem<float>::group_bytes(h->epg, n) * gpb;
-    if (h->blocks < 1) h->blocks = 1;
+    const int og = env_int("DS_PLAN_G", 0), otc = env_int("DS_PLAN_TC", 0);
+    if (og > 0 && otc > 0 && og * n * otc <= cap) { bestG = clampG(og); bestTC = otc; }
+    h->ro_G = bestG; h->ro_TC = bestTC;
+    h->ro_threads = ((bestG * n * bestTC + 31) / 32) * 32;
+    h->ro_blocks = (int)(((long long)E + bestG - 1) / bestG);
+    h->ro_smem = cta_smem(h, bestG, bestTC);
 }
 
 int check_params(const ds_params *p)
@@ -127,11 +180,11 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
         return fail(DS_ERR_ARG, "ds_buffers: pos/vel/reward/true_reward/z/Ni/ncoll must be non-NULL");
     if (integrate && (!io->finished || !io->t))
         return fail(DS_ERR_ARG, "ds_buffers: finished/t must be non-NULL for a step");
-    a->E = h->E; a->n = h->n; a->k = h->k; a->simplify = h->simplify; a->epg = h->epg;
+    a->E = h->E; a->n = h->n; a->k = h->k; a->simplify = h->simplify; a->G = h->step_G;
     a->do_integrate = integrate ? 1 : 0;
     a->log_mode = p->log_mode;
     a->max_steps = p->max_time_steps;
-    a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds};
+    a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds, h->d_thr2, h->d_clipcnt};
     a->dt = p->dt;
     a->q = 2 * p->dt;                        // drone_env.py:269
     a->b = p->collision_weight * p->dt;      // drone_env.py:270
@@ -143,41 +196,45 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
     return DS_OK;
 }
 
+struct Geom { int blocks, threads; size_t smem; };
+
 template <typename KernelT, typename ArgsT>
-int launch(ds_handle *h, KernelT kernel, const ArgsT &args, cudaStream_t st)
+int launch(KernelT kernel, const ArgsT &args, const Geom &gm, cudaStream_t st)
 {
-    if (h->smem > 48 * 1024)
-        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    kernel<<<h->blocks, h->threads, h->smem, st>>>(args);
+    if (gm.smem > 48 * 1024)
+        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
+    kernel<<<gm.blocks, gm.threads, gm.smem, st>>>(args);
     DS_CUDA(cudaGetLastError());
     return DS_OK;
 }
 
-#define DS_DISPATCH_K(KERNEL, REAL, MODE, ARGS)                                           \
+#define DS_DISPATCH_K(KERNEL, REAL, NT, ARGS, GEOM)                                       \
     switch (h->k) {                                                                      \
-    case 0: return launch(h, ds::KERNEL<REAL, 0, MODE>, ARGS, st);                       \
-    case 1: return launch(h, ds::KERNEL<REAL, 1, MODE>, ARGS, st);                       \
-    case 2: return launch(h, ds::KERNEL<REAL, 2, MODE>, ARGS, st);                       \
-    case 3: return launch(h, ds::KERNEL<REAL, 3, MODE>, ARGS, st);                       \
-    case 4: return launch(h, ds::KERNEL<REAL, 4, MODE>, ARGS, st);                       \
-    default: return launch(h, ds::KERNEL<REAL, -1, MODE>, ARGS, st);                     \
+    case 0: return launch(ds::KERNEL<REAL, 0, NT>, ARGS, GEOM, st);                      \
+    case 1: return launch(ds::KERNEL<REAL, 1, NT>, ARGS, GEOM, st);                      \
+    case 2: return launch(ds::KERNEL<REAL, 2, NT>, ARGS, GEOM, st);                      \
+    case 3: return launch(ds::KERNEL<REAL, 3, NT>, ARGS, GEOM, st);                      \
+    case 4: return launch(ds::KERNEL<REAL, 4, NT>, ARGS, GEOM, st);                      \
+    default: return launch(ds::KERNEL<REAL, -1, NT>, ARGS, GEOM, st);                    \
     }
 
-#define DS_DISPATCH_MODE(KERNEL, REAL, ARGS)                                              \
-    if (h->mode == 0) { DS_DISPATCH_K(KERNEL, REAL, 0, ARGS) }                            \
-    else if (h->mode == 1) { DS_DISPATCH_K(KERNEL, REAL, 1, ARGS) }                       \
-    else { DS_DISPATCH_K(KERNEL, REAL, 2, ARGS) }
+#define DS_DISPATCH_NT(KERNEL, REAL, ARGS, GEOM)                                          \
+    if (h->nt == 256) { DS_DISPATCH_K(KERNEL, REAL, 256, ARGS, GEOM) }                    \
+    else { DS_DISPATCH_K(KERNEL, REAL, 1024, ARGS, GEOM) }
+
 
 int launch_step(ds_handle *h, const ds::StepArgs &a, cudaStream_t st)
 {
-    if (h->real_bytes == 8) { DS_DISPATCH_MODE(step_kernel, double, a) }
-    else { DS_DISPATCH_MODE(step_kernel, float, a) }
+    const Geom gm{h->step_blocks, h->step_threads, h->step_smem};
+    if (h->real_bytes == 8) { DS_DISPATCH_NT(step_kernel, double, a, gm) }
+    else { DS_DISPATCH_NT(step_kernel, float, a, gm) }
 }
 
 int launch_rollout(ds_handle *h, const ds::RolloutArgs &a, cudaStream_t st)
 {
-    if (h->real_bytes == 8) { DS_DISPATCH_MODE(rollout_kernel, double, a) }
-    else { DS_DISPATCH_MODE(rollout_kernel, float, a) }
+    const Geom gm{h->ro_blocks, h->ro_threads, h->ro_smem};
+    if (h->real_bytes == 8) { DS_DISPATCH_NT(rollout_kernel, double, a, gm) }
+    else { DS_DISPATCH_NT(rollout_kernel, float, a, gm) }
 }
 
 void free_slots(ds_handle *h)
@@ -256,7 +313,8 @@ int ds_create(const ds_config *cfg, ds_handle **out)
     h->E = cfg->n_envs; h->n = cfg->n_agents; h->k = cfg->k_closest;
     h->simplify = cfg->simplify_zstate ? 1 : 0;
     h->real_bytes = cfg->real_bytes; h->device = cfg->device;
-    h->d_xF = h->d_ds = h->d_delta = h->d_radius = h->d_logds = nullptr;
+    h->d_xF = h->d_ds = h->d_delta = h->d_radius = h->d_logds = h->d_thr2 = nullptr;
+    h->d_clipcnt = nullptr;
     h->act_stage = nullptr; h->act_stage_bytes = 0;
     h->h_radius.assign(cfg->radius, cfg->radius + cfg->n_agents);
     cudaDeviceProp prop;
@@ -266,7 +324,7 @@ int ds_create(const ds_config *cfg, ds_handle **out)
     }
     h->sm_count = prop.multiProcessorCount;
     plan_launch(h);
-    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) {
+    if (h->step_smem > (size_t)prop.sharedMemPerBlockOptin || h->ro_smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete h;
         return fail(DS_ERR_ARG, "ds_create: shared-memory footprint exceeds the device limit");
     }
@@ -281,7 +339,7 @@ void ds_destroy(ds_handle *h)
     if (!h) return;
     DeviceGuard guard(h->device);
     cudaFree(h->d_xF); cudaFree(h->d_ds); cudaFree(h->d_delta); cudaFree(h->d_radius);
-    cudaFree(h->d_logds); cudaFree(h->act_stage);
+    cudaFree(h->d_logds); cudaFree(h->d_thr2); cudaFree(h->d_clipcnt); cudaFree(h->act_stage);
     free_slots(h);
     cudaFree(h->d_agg); cudaFree(h->d_done); cudaFree(h->d_atable);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -321,7 +379,8 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_
     }
     if ((ro->z_tr == nullptr) != (ro->Ni_tr == nullptr))
         return fail(DS_ERR_ARG, "ds_rollout: z_tr and Ni_tr must be given together");
-    ra.T = ro->T; ra.n_actions = ro->n_actions;
+    ra.s.G = h->ro_G;
+    ra.T = ro->T; ra.TC = h->ro_TC; ra.n_actions = ro->n_actions;
     ra.actions = ro->actions; ra.aidx = ro->action_idx; ra.atable = ro->action_table;
     ra.pos_tr = ro->pos_tr; ra.vel_tr = ro->vel_tr; ra.r_tr = ro->reward_tr; ra.tr_tr = ro->true_reward_tr;
     ra.z_tr = ro->z_tr; ra.Ni_tr = ro->Ni_tr; ra.ncoll_tr = ro->ncoll_tr; ra.fin_tr = ro->finished_tr;

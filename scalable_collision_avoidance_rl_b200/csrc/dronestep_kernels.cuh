@@ -1,15 +1,33 @@
 // dronestep_kernels.cuh -- fused sm_100a kernels for the drone_env.step() hot path.
 //
-// One thread per agent.  Agents of one environment live in the same "group":
-//   * n <= 32 : a group is ONE WARP holding floor(32/n) whole environments; the
-//               only synchronisation is __syncwarp (no block barrier on the path);
-//   * n  > 32 : a group is ONE CTA holding max(1, 256/n) whole environments.
-// Positions of a group's environments are staged in shared memory once per step;
-// every thread then walks its row of the n x n distance matrix out of shared
-// memory (broadcast reads), so the matrix itself never exists in memory.  The
-// per-row reductions (barrier sums, Delta-disk count, k+1 nearest) stay in
-// registers; the two per-environment reductions (collision count, all-at-goal)
-// go through one shared-memory counter and flag.
+// Work item = one ROW of one FRAME: agent i of environment e at one time slice.
+// A CTA owns G whole environments and TC consecutive time slices of them
+// (G * n * TC <= blockDim.x items, one item per thread):
+//
+//   * step_kernel     TC = 1: drones.step() / rewards() for E environments.
+//   * rollout_kernel  T fused steps walked in chunks of TC slices.  The
+//       integrator is a single integrator (x <- x + dt u, drone_env.py:78-79,235)
+//       and the actions of a rollout are given up front, so the thread of slice s
+//       re-integrates its own agent from the chunk's start position through the
+//       chunk's actions in shared memory (s+1 sequential, bit-exact additions).
+//       All TC frames of the chunk are then evaluated CONCURRENTLY: time becomes
+//       a parallel axis, which is what fills 148 SMs when E * n is only ~4e4.
+//       Early termination (drone_env.py:248-256) is resolved after the frames are
+//       evaluated and before anything is stored: results of slices behind a
+//       finishing slice are dropped, so the observable behaviour is exactly that
+//       of stepping one slice at a time.
+//
+// A row is evaluated in two passes over the other agents of its frame (positions
+// staged in shared memory; the n x n matrix never exists in memory):
+//   pass 1  squared distance against a per-agent threshold: every pair that is
+//           provably clipped to d_safety (drone_env.py:318 min(.., d_safety[i]))
+//           contributes log(1) = 0, no collision, and a Delta-disk count that is a
+//           per-agent constant -- 6 instructions, no sqrt;
+//   pass 2  only the NEAR pairs (a bit mask per 32 agents) take the exact path:
+//           sqrt, clip, zero rule, division, log, collision test, k-nearest insert.
+// The k+1 nearest are kept in (distance, index) lexicographic order, which is the
+// stable argsort order (drone_env.py:338); clipped agents all tie at d_safety and
+// enter in index order.
 //
 // Reference semantics (file:line in the reference's drone_env.py):
 //   integrate 227-238 | distance_data 295-334 | rewards 260-293 |
@@ -23,55 +41,161 @@
 #include <stdint.h>
 #include <math.h>
 
+#if defined(__CUDA_ARCH__)
+#define DS_DEVICE_CODE 1
+#else
+#define DS_DEVICE_CODE 0
+#endif
+#define DS_HD __host__ __device__ __forceinline__
+
 namespace ds {
 
 constexpr int kMaxK = 16;
 
 // ---------------------------------------------------------------- arithmetic
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
-__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
-__device__ __forceinline__ double log_r(double a) { return log(a); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
-__device__ __forceinline__ float log_r(float a) { return logf(a); }
+// (host branches exist only so that tools/row_check can run the row logic on the
+//  CPU against the oracle; the library itself never computes on the host.)
+DS_HD double add_rn(double a, double b)
+{
+#if DS_DEVICE_CODE
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+DS_HD double sub_rn(double a, double b)
+{
+#if DS_DEVICE_CODE
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+DS_HD double mul_rn(double a, double b)
+{
+#if DS_DEVICE_CODE
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+DS_HD double fma_rn(double a, double b, double c)
+{
+#if DS_DEVICE_CODE
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+DS_HD double div_rn(double a, double b)
+{
+#if DS_DEVICE_CODE
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+DS_HD double sqrt_rn(double a)
+{
+#if DS_DEVICE_CODE
+    return __dsqrt_rn(a);
+#else
+    return sqrt(a);
+#endif
+}
+DS_HD double log_r(double a) { return log(a); }
+DS_HD float add_rn(float a, float b)
+{
+#if DS_DEVICE_CODE
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+DS_HD float sub_rn(float a, float b)
+{
+#if DS_DEVICE_CODE
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+DS_HD float mul_rn(float a, float b)
+{
+#if DS_DEVICE_CODE
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+DS_HD float fma_rn(float a, float b, float c)
+{
+#if DS_DEVICE_CODE
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+DS_HD float div_rn(float a, float b)
+{
+#if DS_DEVICE_CODE
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+DS_HD float sqrt_rn(float a)
+{
+#if DS_DEVICE_CODE
+    return __fsqrt_rn(a);
+#else
+    return sqrtf(a);
+#endif
+}
+DS_HD float log_r(float a) { return logf(a); }
+
+DS_HD int lowest_bit(unsigned m)   // index of the lowest set bit, m != 0
+{
+#if DS_DEVICE_CODE
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
 
 template <typename Real> struct vec2_of;
 template <> struct vec2_of<double> { using type = double2; };
 template <> struct vec2_of<float> { using type = float2; };
 
-template <typename Real> __device__ __forceinline__ Real real_inf();
-template <> __device__ __forceinline__ double real_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
-template <> __device__ __forceinline__ float real_inf<float>() { return __int_as_float(0x7f800000); }
+template <typename Real> DS_HD Real real_inf();
+template <> DS_HD double real_inf<double>() { return (double)INFINITY; }
+template <> DS_HD float real_inf<float>() { return INFINITY; }
 
 // np.nan_to_num (drone_env.py:287-288)
-__device__ __forceinline__ double nan_to_num(double v)
+DS_HD double nan_to_num(double v)
 {
-    if (isnan(v)) return 0.0;
-    if (isinf(v)) return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    if (v != v) return 0.0;
+    if (v > 1.7976931348623157e308) return 1.7976931348623157e308;
+    if (v < -1.7976931348623157e308) return -1.7976931348623157e308;
     return v;
 }
-__device__ __forceinline__ float nan_to_num(float v)
+DS_HD float nan_to_num(float v)
 {
-    if (isnan(v)) return 0.0f;
-    if (isinf(v)) return v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    if (v != v) return 0.0f;
+    if (v > 3.4028234663852886e38f) return 3.4028234663852886e38f;
+    if (v < -3.4028234663852886e38f) return -3.4028234663852886e38f;
     return v;
 }
 
 // ---------------------------------------------------------------- arguments
-struct Consts {              // device arrays of Real, length n (xF: 2n)
+struct Consts {              // device arrays, length n (xF: 2n); Real typed unless noted
     const void *xF, *d_safety, *delta, *radius, *log_ds;
+    const void *thr2;        // Real: pairs with |xi-xj|^2 >= thr2[i] are provably clipped to d_safety[i]
+    const int *clipcnt;      // int: #{j != i : d_safety[i] <= delta[j]}  (Delta-disk count of clipped pairs)
 };
 
 struct StepArgs {
-    int E, n, k, simplify, epg, do_integrate, log_mode, max_steps;
+    int E, n, k, simplify, G, do_integrate, log_mode, max_steps;
     Consts c;
     double dt, q, b, goal_tol, sentinel, zero_eps, ghost;
     const void *act;         // Real [E][n][2]
@@ -83,7 +207,7 @@ struct StepArgs {
 
 struct RolloutArgs {
     StepArgs s;
-    int T, n_actions;
+    int T, TC, n_actions;
     const void *actions;     // Real [T][E][n][2] or null
     const uint8_t *aidx;     // u8 [T][E][n]
     const void *atable;      // Real [n_actions][2]
@@ -97,18 +221,19 @@ struct RolloutArgs {
 template <typename Real> struct ParamsR {
     Real dt, q, b, goal_tol, sentinel, zero_eps, ghost;
     int log_mode, simplify, k;
-    __device__ explicit ParamsR(const StepArgs &a)
+    DS_HD explicit ParamsR(const StepArgs &a)
         : dt((Real)a.dt), q((Real)a.q), b((Real)a.b), goal_tol((Real)a.goal_tol),
           sentinel((Real)a.sentinel), zero_eps((Real)a.zero_eps), ghost((Real)a.ghost),
           log_mode(a.log_mode), simplify(a.simplify), k(a.k) {}
 };
 
 template <typename Real> struct AgentConst {   // per-thread (row i) constants
-    Real xF, yF, ds, delta, radius, log_ds;
+    Real xF, yF, ds, delta, radius, log_ds, thr2;
+    int clipcnt;
 };
 
 template <typename Real>
-__device__ __forceinline__ AgentConst<Real> load_agent_const(const Consts &c, int i)
+DS_HD AgentConst<Real> load_agent_const(const Consts &c, int i)
 {
     AgentConst<Real> a;
     a.xF = ((const Real *)c.xF)[2 * i];
@@ -117,12 +242,14 @@ __device__ __forceinline__ AgentConst<Real> load_agent_const(const Consts &c, in
     a.delta = ((const Real *)c.delta)[i];
     a.radius = ((const Real *)c.radius)[i];
     a.log_ds = ((const Real *)c.log_ds)[i];
+    a.thr2 = ((const Real *)c.thr2)[i];
+    a.clipcnt = c.clipcnt[i];
     return a;
 }
 
 // ---------------------------------------------------------------- one row of the pair matrix
 // Everything rewards() derives for agent i (drone_env.py:260-293) from the staged
-// positions of its environment.
+// positions of its frame.
 template <typename Real, int K> struct RowResult {
     static constexpr int CAP = (K >= 0 ? K : kMaxK) + 1;
     Real r, tr;          // localized / global reward
@@ -134,57 +261,104 @@ template <typename Real, int K> struct RowResult {
     int tj[CAP];
 };
 
+// Offer (d, j) to the k+1 smallest kept in (d, j) lexicographic order -- the order
+// a stable argsort of row i produces (np.argsort row, :338).  Returns false when
+// the candidate does not make the list.
 template <typename Real, int K>
-__device__ __forceinline__ void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
-                                         const AgentConst<Real> &c,
-                                         const typename vec2_of<Real>::type *__restrict__ s_pos,
-                                         const Real *__restrict__ s_delta,
-                                         const Real *__restrict__ s_radius,
-                                         const ParamsR<Real> &P)
+DS_HD bool topk_offer(RowResult<Real, K> &o, int kk, Real d, int j)
 {
+    constexpr int CAP = RowResult<Real, K>::CAP;
+    if (!(d < o.td[kk] || (d == o.td[kk] && j < o.tj[kk]))) return false;
+    o.td[kk] = d; o.tj[kk] = j;
+#pragma unroll
+    for (int m = CAP - 1; m > 0; --m) {
+        if (m <= kk) {
+            const bool lt = o.td[m] < o.td[m - 1] || (o.td[m] == o.td[m - 1] && o.tj[m] < o.tj[m - 1]);
+            if (lt) {
+                const Real tdv = o.td[m]; o.td[m] = o.td[m - 1]; o.td[m - 1] = tdv;
+                const int tjv = o.tj[m]; o.tj[m] = o.tj[m - 1]; o.tj[m - 1] = tjv;
+            }
+        }
+    }
+    return true;
+}
+
+template <typename Real, int K>
+DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
+                    const AgentConst<Real> &c,
+                    const typename vec2_of<Real>::type *__restrict__ s_pos,
+                    const Real *__restrict__ s_delta,
+                    const Real *__restrict__ s_radius,
+                    const ParamsR<Real> &P)
+{
+    using V2 = typename vec2_of<Real>::type;
     const int kk = (K >= 0) ? K : P.k;
     constexpr int CAP = RowResult<Real, K>::CAP;
 #pragma unroll
     for (int m = 0; m < CAP; ++m) { o.td[m] = real_inf<Real>(); o.tj[m] = 0; }
 
     Real sum_local = 0, sum_all = 0;
-    int ncoll = 0, cnt_nd = 0;
-#pragma unroll 2
-    for (int j = 0; j < n; ++j) {
-        const typename vec2_of<Real>::type pj = s_pos[j];
-        const Real dx = sub_rn(xi, pj.x), dy = sub_rn(yi, pj.y);
-        const Real dist = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));       // :318 (BLAS ddot)
-        const Real raw = sub_rn(sub_rn(dist, c.radius), s_radius[j]);     // :318 / :323 (dist == 0)
-        Real d = (c.ds < raw) ? c.ds : raw;                               // python min(raw, d_safety[i])
-        const bool self = (j == i);
-        if (!self && d == (Real)0) d = P.zero_eps;                        // :319-320
-        cnt_nd += (d <= s_delta[j]) ? 1 : 0;                              // :328 deltas[j]
-        if (!self && d != c.ds) {
-            // not clipped: d_ij_norm != 1, the barrier term is live (:321,327,330-332)
-            Real logd;
-            bool coll;
-            if (P.log_mode == 0) {
-                const Real dn = div_rn(c.ds, d);
-                coll = dn <= (Real)0;
-                logd = coll ? P.sentinel : log_r(dn);
-            } else {
-                coll = (c.ds > (Real)0) ? (d < (Real)0) : (c.ds == (Real)0);
-                logd = coll ? P.sentinel : sub_rn(c.log_ds, log_r(fabs(d)));
-            }
-            ncoll += coll ? 1 : 0;
-            sum_all = add_rn(sum_all, logd);                                                   // :283
-            sum_local = add_rn(sum_local, mul_rn(logd, (d <= s_delta[j]) ? (Real)1 : (Real)0)); // :282
+    int ncoll = 0;
+    // j == i (:323-325): dist = 0, d_ii = min(-2 l_i, d_safety[i]), d_norm = 1 -> no barrier term
+    const Real raw_ii = sub_rn(sub_rn((Real)0, c.radius), c.radius);
+    const Real d_ii = (c.ds < raw_ii) ? c.ds : raw_ii;
+    int cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);               // :328 deltas[j], j == i
+    const bool self_unclipped = (d_ii != c.ds);
+    if (d_ii < c.ds) topk_offer<Real, K>(o, kk, d_ii, i);
+
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int jn = (n - j0 < 32) ? (n - j0) : 32;
+        // pass 1: which agents of this block of 32 are NOT provably clipped
+        unsigned near = 0;
+#pragma unroll 4
+        for (int jj = 0; jj < jn; ++jj) {
+            const V2 pj = s_pos[j0 + jj];
+            const Real dx = sub_rn(xi, pj.x), dy = sub_rn(yi, pj.y);
+            const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
+            near |= ((d2 >= c.thr2) ? 0u : 1u) << jj;                   // NaN -> near (exact path)
         }
-        // running k+1 smallest (np.argsort row, :338): strict '<' keeps the lower index on ties
-        if (d < o.td[kk]) {
-            o.td[kk] = d; o.tj[kk] = j;
-#pragma unroll
-            for (int m = CAP - 1; m > 0; --m) {
-                if (m <= kk && o.td[m] < o.td[m - 1]) {
-                    const Real tdv = o.td[m]; o.td[m] = o.td[m - 1]; o.td[m - 1] = tdv;
-                    const int tjv = o.tj[m]; o.tj[m] = o.tj[m - 1]; o.tj[m - 1] = tjv;
+        const unsigned selfbit = ((unsigned)(i - j0) < 32u) ? (1u << (i - j0)) : 0u;
+        near &= ~selfbit;
+        unsigned unclipped = self_unclipped ? selfbit : 0u;             // agents with d_ij != d_safety[i]
+        // pass 2: exact evaluation of the near pairs, ascending j (summation order of :282-283)
+        while (near) {
+            const int jj = lowest_bit(near);
+            near &= near - 1;
+            const int j = j0 + jj;
+            const V2 pj = s_pos[j];
+            const Real dx = sub_rn(xi, pj.x), dy = sub_rn(yi, pj.y);
+            const Real dist = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));     // :318 (BLAS ddot)
+            const Real raw = sub_rn(sub_rn(dist, c.radius), s_radius[j]);   // :318
+            Real d = (c.ds < raw) ? c.ds : raw;                             // python min(raw, d_safety[i])
+            if (d == (Real)0) d = P.zero_eps;                               // :319-320
+            const Real dl = s_delta[j];
+            const bool in_disk = d <= dl;                                   // :328 deltas[j]
+            cnt_nd += (in_disk ? 1 : 0) - ((c.ds <= dl) ? 1 : 0);           // replaces the clipped-pair count
+            if (d != c.ds) {
+                // not clipped: d_ij_norm != 1, the barrier term is live (:321,327,330-332)
+                unclipped |= 1u << jj;
+                Real logd;
+                bool coll;
+                if (P.log_mode == 0) {
+                    const Real dn = div_rn(c.ds, d);
+                    coll = dn <= (Real)0;
+                    logd = coll ? P.sentinel : log_r(dn);
+                } else {
+                    coll = (c.ds > (Real)0) ? (d < (Real)0) : (c.ds == (Real)0);
+                    logd = coll ? P.sentinel : sub_rn(c.log_ds, log_r(fabs(d)));
                 }
+                ncoll += coll ? 1 : 0;
+                sum_all = add_rn(sum_all, logd);                                                 // :283
+                sum_local = add_rn(sum_local, mul_rn(logd, in_disk ? (Real)1 : (Real)0));        // :282
+                if (d < c.ds) topk_offer<Real, K>(o, kk, d, j);
             }
+        }
+        // clipped agents tie at exactly d_safety[i]: offered in index order until one is refused
+        unsigned cm = ((jn == 32) ? 0xffffffffu : ((1u << jn) - 1u)) & ~unclipped;
+        while (cm) {
+            const int jj = lowest_bit(cm);
+            if (!topk_offer<Real, K>(o, kk, c.ds, j0 + jj)) break;
+            cm &= cm - 1;
         }
     }
     const Real gx = sub_rn(c.xF, xi), gy = sub_rn(c.yF, yi);
@@ -200,13 +374,13 @@ __device__ __forceinline__ void eval_row(RowResult<Real, K> &o, int n, int i, Re
 
 // Write z_i (k+1 rows) and Ni_i (drone_env.py:344-397) for global agent index g.
 template <typename Real, int K>
-__device__ __forceinline__ void write_obs(const RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
-                                          const AgentConst<Real> &c,
-                                          const typename vec2_of<Real>::type *__restrict__ s_pos,
-                                          const typename vec2_of<Real>::type *__restrict__ s_vel,
-                                          const Real *__restrict__ s_radius,
-                                          const ParamsR<Real> &P, Real *__restrict__ z, int *__restrict__ Ni,
-                                          size_t g)
+DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
+                     const AgentConst<Real> &c,
+                     const typename vec2_of<Real>::type *__restrict__ s_pos,
+                     const typename vec2_of<Real>::type *__restrict__ s_vel,
+                     const Real *__restrict__ s_radius,
+                     const ParamsR<Real> &P, Real *__restrict__ z, int *__restrict__ Ni,
+                     size_t g)
 {
     using V2 = typename vec2_of<Real>::type;
     const int kk = (K >= 0) ? K : P.k;
@@ -271,72 +445,59 @@ __device__ __forceinline__ void write_obs(const RowResult<Real, K> &o, int n, in
     for (; nn <= kk; ++nn) nl[nn] = -1;
 }
 
-// ---------------------------------------------------------------- group plumbing
-// MODE 0: group = warp (CTA of 4 warps); MODE 1: group = CTA of <= 256 threads;
-// MODE 2: group = CTA of <= 1024 threads (n > 256; register-capped at 64).
-template <int MODE> __device__ __forceinline__ void group_sync()
-{
-    if (MODE == 0) __syncwarp(); else __syncthreads();
-}
-constexpr int mode_max_threads(int mode) { return mode == 0 ? 128 : (mode == 1 ? 256 : 1024); }
-
-// Shared-memory carve-up.  Block-wide: delta[n], radius[n].  Per group:
-// pos[epg*n] vec2, vel[epg*n] vec2, rsum[2][epg*n] Real, cnt[2][epg] int, notgoal[2][epg] int.
-template <typename Real> struct GroupSmem {
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------- shared-memory carve-up
+// CTA-wide: delta[n], radius[n].  Per item (TC*G*n): act/vel, pos, r, tr.  Per agent of a
+// slice (G*n): chunk start position, last executed velocity.  Per frame (TC*G): collision
+// count, not-at-goal flag, per-frame means.  Per environment (G): alive, t, executed slices.
+template <typename Real> struct CtaSmem {
     using V2 = typename vec2_of<Real>::type;
     Real *delta, *radius;
-    V2 *pos, *vel;
+    V2 *act, *pos, *p0, *vfin;
     Real *r, *tr;
-    int *cnt, *notgoal;
-    __host__ __device__ static size_t group_bytes(int epg, int n)
+    double *mr, *mtr;
+    int *cnt, *notgoal, *mc, *alive, *tenv, *nexec;
+    __host__ __device__ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+    __host__ __device__ static size_t bytes(int n, int G, int TC)
     {
-        size_t agents = (size_t)epg * n;
-        size_t b = agents * sizeof(V2) * 2 + agents * sizeof(Real) * 2 + (size_t)epg * sizeof(int) * 4;
-        return (b + 15) & ~(size_t)15;
+        const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
+        return align16(2 * n * sizeof(Real)) + 2 * I * sizeof(V2) + 2 * A * sizeof(V2) +
+               align16(2 * I * sizeof(Real)) + 2 * F * sizeof(double) + align16(3 * F * sizeof(int)) +
+               align16(3 * (size_t)G * sizeof(int));
     }
-    __host__ __device__ static size_t const_bytes(int n)
+    __device__ CtaSmem(unsigned char *base, int n, int G, int TC)
     {
-        return (((size_t)n * sizeof(Real) * 2) + 15) & ~(size_t)15;
-    }
-    __device__ GroupSmem(unsigned char *base, int epg, int n, int group_in_block)
-    {
-        delta = reinterpret_cast<Real *>(base);
-        radius = delta + n;
-        unsigned char *g = base + const_bytes(n) + group_bytes(epg, n) * group_in_block;
-        const size_t agents = (size_t)epg * n;
-        pos = reinterpret_cast<V2 *>(g);
-        vel = pos + agents;
-        r = reinterpret_cast<Real *>(vel + agents);
-        tr = r + agents;
-        cnt = reinterpret_cast<int *>(tr + agents);
-        notgoal = cnt + 2 * epg;
+        const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
+        unsigned char *p = base;
+        delta = reinterpret_cast<Real *>(p); radius = delta + n; p += align16(2 * n * sizeof(Real));
+        act = reinterpret_cast<V2 *>(p); pos = act + I; p0 = pos + I; vfin = p0 + A;
+        p += 2 * I * sizeof(V2) + 2 * A * sizeof(V2);
+        r = reinterpret_cast<Real *>(p); tr = r + I; p += align16(2 * I * sizeof(Real));
+        mr = reinterpret_cast<double *>(p); mtr = mr + F; p += 2 * F * sizeof(double);
+        cnt = reinterpret_cast<int *>(p); notgoal = cnt + F; mc = notgoal + F; p += align16(3 * F * sizeof(int));
+        alive = reinterpret_cast<int *>(p); tenv = alive + G; nexec = tenv + G;
     }
 };
 
 // ---------------------------------------------------------------- step kernel
-// drones.step() / rewards() for E environments, one launch.
-template <typename Real, int K, int MODE>
-__global__ void __launch_bounds__(mode_max_threads(MODE))
+// drones.step() / rewards() for E environments, one launch; CTA = G environments.
+template <typename Real, int K, int NT>
+__global__ void __launch_bounds__(NT)
 step_kernel(const StepArgs a)
 {
     using V2 = typename vec2_of<Real>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = a.n, epg = a.epg;
-    constexpr bool WARP = (MODE == 0);
-    const int gib = WARP ? (threadIdx.x >> 5) : 0;
-    const int lt = WARP ? (threadIdx.x & 31) : threadIdx.x;
-    const int group = WARP ? (blockIdx.x * (blockDim.x >> 5) + gib) : blockIdx.x;
-    GroupSmem<Real> sm(smem_raw, epg, n, gib);
+    const int n = a.n, G = a.G;
+    CtaSmem<Real> sm(smem_raw, n, G, 1);
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         sm.delta[idx] = ((const Real *)a.c.delta)[idx];
         sm.radius[idx] = ((const Real *)a.c.radius)[idx];
     }
-    __syncthreads();
-
     const ParamsR<Real> P(a);
+    const int lt = threadIdx.x;
     const int le = lt / n, i = lt - le * n;
-    const long long e = (long long)group * epg + le;
-    const bool active = (lt < epg * n) && (e < a.E);
+    const long long e = (long long)blockIdx.x * G + le;
+    const bool active = (lt < G * n) && (e < a.E);
     const size_t g = active ? (size_t)e * n + i : 0;
 
     Real xi = 0, yi = 0;
@@ -357,21 +518,21 @@ step_kernel(const StepArgs a)
         }
         xi = p.x; yi = p.y;
         sm.pos[lt] = p;
-        sm.vel[lt] = v;
+        sm.act[lt] = v;
         if (i == 0) { sm.cnt[le] = 0; sm.notgoal[le] = 0; }
     }
-    group_sync<MODE>();
+    __syncthreads();
     if (active) {
         RowResult<Real, K> o;
         eval_row<Real, K>(o, n, i, xi, yi, c, sm.pos + le * n, sm.delta, sm.radius, P);
         reinterpret_cast<Real *>(a.r)[g] = o.r;
         reinterpret_cast<Real *>(a.tr)[g] = o.tr;
-        write_obs<Real, K>(o, n, i, xi, yi, c, sm.pos + le * n, sm.vel + le * n, sm.radius, P,
+        write_obs<Real, K>(o, i, xi, yi, c, sm.pos + le * n, sm.act + le * n, sm.radius, P,
                            reinterpret_cast<Real *>(a.z), a.Ni, g);
         if (o.ncoll) atomicAdd(&sm.cnt[le], o.ncoll);
         if (!o.at_goal) sm.notgoal[le] = 1;
     }
-    group_sync<MODE>();
+    __syncthreads();
     if (active && i == 0) {
         a.ncoll[e] = sm.cnt[le];                                           // :284
         if (a.do_integrate) {
@@ -383,50 +544,49 @@ step_kernel(const StepArgs a)
 }
 
 // ---------------------------------------------------------------- rollout kernel
-// T fused steps: positions stay in registers / shared memory between steps, the
-// action stream is read from HBM (prefetched one step ahead) and every step's
-// outputs are streamed to the trajectory buffers.
-template <typename Real, int K, int MODE>
-__global__ void __launch_bounds__(mode_max_threads(MODE))
+// T fused steps, TC time slices per chunk evaluated concurrently (see the header comment).
+template <typename Real, int K, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
 rollout_kernel(const RolloutArgs ra)
 {
     using V2 = typename vec2_of<Real>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StepArgs &a = ra.s;
-    const int n = a.n, epg = a.epg, E = a.E;
-    constexpr bool WARP = (MODE == 0);
-    const int gib = WARP ? (threadIdx.x >> 5) : 0;
-    const int lt = WARP ? (threadIdx.x & 31) : threadIdx.x;
-    const int group = WARP ? (blockIdx.x * (blockDim.x >> 5) + gib) : blockIdx.x;
-    GroupSmem<Real> sm(smem_raw, epg, n, gib);
+    const int n = a.n, G = a.G, TC = ra.TC, E = a.E, T = ra.T;
+    CtaSmem<Real> sm(smem_raw, n, G, TC);
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         sm.delta[idx] = ((const Real *)a.c.delta)[idx];
         sm.radius[idx] = ((const Real *)a.c.radius)[idx];
     }
-    __syncthreads();
-
     const ParamsR<Real> P(a);
     const int kk = (K >= 0) ? K : a.k;
     const int cols = a.simplify ? 2 : 5;
-    const int le = lt / n, i = lt - le * n;
-    const long long e = (long long)group * epg + le;
-    const bool active = (lt < epg * n) && (e < E);
+    const int A = G * n;                              // agents per slice in this CTA
+    const int tid = threadIdx.x;
+    const int s = tid / A, ag = tid - s * A;          // time slice within the chunk, agent slot
+    const int le = ag / n, i = ag - le * n;
+    const long long e = (long long)blockIdx.x * G + le;
+    const bool active = (s < TC) && (e < E);
     const size_t g = active ? (size_t)e * n + i : 0;
     const size_t EN = (size_t)E * n;
+    const int fr = s * G + le;                        // frame slot of this thread
+    const V2 *atab = reinterpret_cast<const V2 *>(ra.atable);
 
     AgentConst<Real> c{};
-    V2 p{}, v{};
-    bool alive = false;
-    int tt = 0;
-    if (active) {
-        c = load_agent_const<Real>(a.c, i);
-        p = reinterpret_cast<const V2 *>(a.pos)[g];
-        v = reinterpret_cast<const V2 *>(a.vel)[g];
-        alive = ra.done[e] == 0;
-        tt = a.t[e];
+    if (active) c = load_agent_const<Real>(a.c, i);
+    if (active && s == 0) {
+        sm.p0[ag] = reinterpret_cast<const V2 *>(a.pos)[g];
+        sm.vfin[ag] = reinterpret_cast<const V2 *>(a.vel)[g];
+        if (i == 0) { sm.alive[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv[le] = a.t[e]; sm.nexec[le] = 0; }
     }
+    // per-environment episode accumulators live in one thread (s == 0, i == 0)
+    const bool acc_thread = active && s == 0 && i == 0;
     double acc_r = 0, acc_tr = 0, acc_c = 0, acc_s = 0;
-    const V2 *atab = reinterpret_cast<const V2 *>(ra.atable);
+    if (acc_thread) {
+        const double *ag4 = ra.agg + (size_t)e * 4;
+        acc_r = ag4[0]; acc_tr = ag4[1]; acc_c = ag4[2]; acc_s = ag4[3];
+    }
+    bool stepped = false;
 
     auto load_action = [&](int t) -> V2 {
         const size_t at = (size_t)t * EN + g;
@@ -434,72 +594,108 @@ rollout_kernel(const RolloutArgs ra)
         return atab[ra.aidx[at]];
     };
     V2 u_next{};
-    if (alive && ra.T > 0) u_next = load_action(0);
+    if (active && s < T) u_next = load_action(s);
 
-    for (int t = 0; t < ra.T; ++t) {
-        const int buf = t & 1;
-        const size_t at = (size_t)t * EN + g;
-        if (alive) {
-            const V2 u = u_next;
-            if (t + 1 < ra.T) u_next = load_action(t + 1);   // prefetch: hides the HBM latency
-            p.x = add_rn(p.x, mul_rn(P.dt, u.x));
-            p.y = add_rn(p.y, mul_rn(P.dt, u.y));
-            v = u;
-            sm.pos[lt] = p;
-            sm.vel[lt] = v;
-            if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
-            if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = v;
-            if (i == 0) { sm.cnt[buf * epg + le] = 0; sm.notgoal[buf * epg + le] = 0; }
-        } else if (active && i == 0 && ra.fin_tr) {
-            ra.fin_tr[(size_t)t * E + e] = 2;
+    for (int t0 = 0; t0 < T; t0 += TC) {
+        const int nsl = (T - t0 < TC) ? (T - t0) : TC;      // slices in this chunk
+        const bool in_chunk = active && s < nsl;
+        const V2 u = u_next;
+        if (active && t0 + TC + s < T) u_next = load_action(t0 + TC + s);   // prefetch the next chunk
+        if (in_chunk) sm.act[tid] = u;
+        __syncthreads();                                     // (1) actions, p0, alive, tenv visible
+        // episode accumulators of the PREVIOUS chunk, in time order (train_problem.py:98-100)
+        if (acc_thread) {
+            const int ne = sm.nexec[le];
+            for (int q = 0; q < ne; ++q) {
+                acc_r += sm.mr[q * G + le]; acc_tr += sm.mtr[q * G + le];
+                acc_c += (double)sm.mc[q * G + le]; acc_s += 1;
+            }
+            if (ne) stepped = true;
+            sm.nexec[le] = 0;
         }
-        group_sync<MODE>();
+        const bool valid = in_chunk && sm.alive[le] != 0;
+        const int tt0 = active ? sm.tenv[le] : 0;
+        V2 p{};
+        if (valid) {
+            p = sm.p0[ag];
+            for (int q = 0; q <= s; ++q) {                   // s+1 sequential single-integrator steps
+                const V2 uq = sm.act[q * A + ag];
+                p.x = add_rn(p.x, mul_rn(P.dt, uq.x));      // A = I, B = dt I (:78-79,235)
+                p.y = add_rn(p.y, mul_rn(P.dt, uq.y));
+            }
+            sm.pos[tid] = p;
+            if (i == 0) { sm.cnt[fr] = 0; sm.notgoal[fr] = 0; }
+        }
+        __syncthreads();                                     // (2) positions of every frame staged
         RowResult<Real, K> o;
-        if (alive) {
-            eval_row<Real, K>(o, n, i, p.x, p.y, c, sm.pos + le * n, sm.delta, sm.radius, P);
-            if (ra.r_tr) reinterpret_cast<Real *>(ra.r_tr)[at] = o.r;
-            if (ra.tr_tr) reinterpret_cast<Real *>(ra.tr_tr)[at] = o.tr;
-            if (ra.z_tr)
-                write_obs<Real, K>(o, n, i, p.x, p.y, c, sm.pos + le * n, sm.vel + le * n, sm.radius, P,
-                                   reinterpret_cast<Real *>(ra.z_tr) + (size_t)t * EN * (kk + 1) * cols,
-                                   ra.Ni_tr + (size_t)t * EN * (kk + 1), g);
-            sm.r[lt] = o.r;
-            sm.tr[lt] = o.tr;
-            if (o.ncoll) atomicAdd(&sm.cnt[buf * epg + le], o.ncoll);
-            if (!o.at_goal) sm.notgoal[buf * epg + le] = 1;
+        if (valid) {
+            eval_row<Real, K>(o, n, i, p.x, p.y, c, sm.pos + s * A + le * n, sm.delta, sm.radius, P);
+            sm.r[tid] = o.r;
+            sm.tr[tid] = o.tr;
+            if (o.ncoll) atomicAdd(&sm.cnt[fr], o.ncoll);
+            if (!o.at_goal) sm.notgoal[fr] = 1;
         }
-        group_sync<MODE>();
-        if (alive) {
-            const int nc = sm.cnt[buf * epg + le];
-            const bool fin = (sm.notgoal[buf * epg + le] == 0) || (tt >= a.max_steps - 1);
-            tt += 1;
-            if (i == 0) {
-                if (ra.ncoll_tr) ra.ncoll_tr[(size_t)t * E + e] = nc;
-                if (ra.fin_tr) ra.fin_tr[(size_t)t * E + e] = fin ? 1 : 0;
-                double sr = 0, st = 0;
-                for (int j = 0; j < n; ++j) { sr += (double)sm.r[le * n + j]; st += (double)sm.tr[le * n + j]; }
-                acc_r += sr / n; acc_tr += st / n; acc_c += nc; acc_s += 1;   // train_problem.py:98-100
+        __syncthreads();                                     // (3) per-frame reductions complete
+        const size_t at = (size_t)(t0 + s) * EN + g;
+        const size_t fe = (size_t)(t0 + s) * E + (size_t)e;
+        if (valid) {
+            // a slice executes iff no earlier slice of this chunk finished the episode (:248-256)
+            bool exec = true;
+            for (int q = 0; q < s; ++q)
+                if (sm.notgoal[q * G + le] == 0 || tt0 + q >= a.max_steps - 1) exec = false;
+            if (exec) {
+                const int nc = sm.cnt[fr];
+                const bool fin = (sm.notgoal[fr] == 0) || (tt0 + s >= a.max_steps - 1);
+                const bool last = fin || (s == nsl - 1);     // last executed slice of this chunk
+                const V2 *fpos = sm.pos + s * A + le * n, *fvel = sm.act + s * A + le * n;
+                if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
+                if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = u;              // :238
+                if (ra.r_tr) reinterpret_cast<Real *>(ra.r_tr)[at] = o.r;
+                if (ra.tr_tr) reinterpret_cast<Real *>(ra.tr_tr)[at] = o.tr;
+                if (ra.z_tr)
+                    write_obs<Real, K>(o, i, p.x, p.y, c, fpos, fvel, sm.radius, P,
+                                       reinterpret_cast<Real *>(ra.z_tr) + (size_t)(t0 + s) * EN * (kk + 1) * cols,
+                                       ra.Ni_tr + (size_t)(t0 + s) * EN * (kk + 1), g);
+                if (last) { sm.p0[ag] = p; sm.vfin[ag] = u; }
+                if (fin || t0 + s == T - 1) {
+                    // last executed step of the call: leave the step()-style outputs in the live buffers
+                    reinterpret_cast<Real *>(a.r)[g] = o.r;
+                    reinterpret_cast<Real *>(a.tr)[g] = o.tr;
+                    write_obs<Real, K>(o, i, p.x, p.y, c, fpos, fvel, sm.radius, P,
+                                       reinterpret_cast<Real *>(a.z), a.Ni, g);
+                    if (i == 0) { a.ncoll[e] = nc; a.fin[e] = fin ? 1 : 0; }
+                }
+                if (i == 0) {
+                    if (ra.ncoll_tr) ra.ncoll_tr[fe] = nc;
+                    if (ra.fin_tr) ra.fin_tr[fe] = fin ? 1 : 0;
+                    double sr = 0, st = 0;
+                    for (int j = 0; j < n; ++j) { sr += (double)sm.r[s * A + le * n + j]; st += (double)sm.tr[s * A + le * n + j]; }
+                    sm.mr[fr] = sr / n; sm.mtr[fr] = st / n; sm.mc[fr] = nc;
+                    if (last) { sm.nexec[le] = s + 1; sm.tenv[le] = tt0 + s + 1; if (fin) sm.alive[le] = 0; }
+                }
+            } else if (i == 0 && ra.fin_tr) {
+                ra.fin_tr[fe] = 2;
             }
-            if (fin || t == ra.T - 1) {
-                // last executed step: leave the step()-style outputs in the live buffers
-                reinterpret_cast<Real *>(a.r)[g] = o.r;
-                reinterpret_cast<Real *>(a.tr)[g] = o.tr;
-                write_obs<Real, K>(o, n, i, p.x, p.y, c, sm.pos + le * n, sm.vel + le * n, sm.radius, P,
-                                   reinterpret_cast<Real *>(a.z), a.Ni, g);
-                if (i == 0) { a.ncoll[e] = nc; a.fin[e] = fin ? 1 : 0; }
-            }
-            if (fin) alive = false;
+        } else if (in_chunk && i == 0 && ra.fin_tr) {
+            ra.fin_tr[fe] = 2;
         }
     }
-    if (active) {
-        reinterpret_cast<V2 *>(a.pos)[g] = p;
-        reinterpret_cast<V2 *>(a.vel)[g] = v;
+    __syncthreads();
+    if (active && s == 0) {
+        reinterpret_cast<V2 *>(a.pos)[g] = sm.p0[ag];
+        reinterpret_cast<V2 *>(a.vel)[g] = sm.vfin[ag];
         if (i == 0) {
-            a.t[e] = tt;
-            if (acc_s > 0) {
-                if (!alive) ra.done[e] = 1;
-                double *ag = ra.agg + (size_t)e * 4;
-                ag[0] += acc_r; ag[1] += acc_tr; ag[2] += acc_c; ag[3] += acc_s;
+            const int ne = sm.nexec[le];
+            for (int q = 0; q < ne; ++q) {
+                acc_r += sm.mr[q * G + le]; acc_tr += sm.mtr[q * G + le];
+                acc_c += (double)sm.mc[q * G + le]; acc_s += 1;
+            }
+            if (ne) stepped = true;
+            a.t[e] = sm.tenv[le];
+            if (stepped) {
+                if (sm.alive[le] == 0) ra.done[e] = 1;
+                double *ag4 = ra.agg + (size_t)e * 4;
+                ag4[0] = acc_r; ag4[1] = acc_tr; ag4[2] = acc_c; ag4[3] = acc_s;
             }
         }
     }
@@ -525,5 +721,6 @@ __global__ void __launch_bounds__(1024) reduce_agg_kernel(const double *__restri
     if (threadIdx.x < 4) out[threadIdx.x] = s[threadIdx.x][0];
     if (threadIdx.x == 4) out[4] = (double)E;
 }
+#endif  // __CUDACC__
 
 }  // namespace ds
