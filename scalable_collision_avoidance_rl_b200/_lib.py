@@ -73,7 +73,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # DS_LIB_OVERRIDE: another build of the same sources (kernel tuning experiments only)
+    return os.environ.get("DS_LIB_OVERRIDE") or _build.LIB_PATH
 
 
 def load():

@@ -41,11 +41,13 @@ struct ds_handle {
     int step_G, step_threads, step_blocks;
     size_t step_smem;
     int ro_G, ro_TC, ro_threads, ro_blocks;
+    int ro_L, ro_NB;          // work-list capacity; near-mask words kept in registers (0 = any n)
     size_t ro_smem;
     size_t smem_optin;
     // device constants (Real typed unless noted)
     void *d_xF, *d_ds, *d_delta, *d_radius, *d_logds, *d_thr2;
     int *d_clipcnt;
+    ds::LogTabEntry *d_logtab;
     std::vector<double> h_radius;
     // staging for the host-buffer entries
     void *act_stage;
@@ -117,6 +119,10 @@ int upload_consts(ds_handle *h, const ds_config *cfg)
     DS_CUDA(cudaMemcpy(h->d_logds, lg.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
     DS_CUDA(cudaMemcpy(h->d_thr2, thr2.data(), sizeof(Real) * n, cudaMemcpyHostToDevice));
     DS_CUDA(cudaMemcpy(h->d_clipcnt, clipcnt.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    std::vector<ds::LogTabEntry> tab(ds::kLogTabSize);
+    ds::fill_log_table(tab.data());
+    DS_CUDA(cudaMalloc((void **)&h->d_logtab, sizeof(ds::LogTabEntry) * ds::kLogTabSize));
+    DS_CUDA(cudaMemcpy(h->d_logtab, tab.data(), sizeof(ds::LogTabEntry) * ds::kLogTabSize, cudaMemcpyHostToDevice));
     return DS_OK;
 }
 
@@ -129,6 +135,11 @@ int env_int(const char *name, int dflt)
 size_t cta_smem(const ds_handle *h, int G, int TC)
 {
     return h->real_bytes == 8 ? ds::CtaSmem<double>::bytes(h->n, G, TC) : ds::CtaSmem<float>::bytes(h->n, G, TC);
+}
+
+size_t rollout_smem(const ds_handle *h, int G, int TC, int L)
+{
+    return h->real_bytes == 8 ? ds::RoSmem<double>::bytes(h->n, G, TC, L) : ds::RoSmem<float>::bytes(h->n, G, TC, L);
 }
 
 // One item (agent of one environment at one time slice) per thread.  step: CTA = G whole
@@ -158,7 +169,16 @@ void plan_launch(ds_handle *h)
     h->ro_G = bestG; h->ro_TC = bestTC;
     h->ro_threads = ((bestG * n * bestTC + 31) / 32) * 32;
     h->ro_blocks = (int)(((long long)E + bestG - 1) / bestG);
-    h->ro_smem = cta_smem(h, bestG, bestTC);
+    // work list: room for DS_PLAN_LPR (default 6) near pairs per row; rows that do not fit
+    // evaluate themselves (correct for any density, slower)
+    int per_row = (n - 1 < env_int("DS_PLAN_LPR", 6)) ? (n - 1) : env_int("DS_PLAN_LPR", 6);
+    per_row = per_row < 1 ? 1 : per_row;
+    h->ro_NB = n <= 32 ? 1 : (n <= 128 ? 4 : 0);
+    for (;; --per_row) {
+        h->ro_L = bestG * n * bestTC * per_row;
+        h->ro_smem = rollout_smem(h, bestG, bestTC, h->ro_L);
+        if (h->ro_smem <= h->smem_optin || per_row == 1) break;
+    }
 }
 
 int check_params(const ds_params *p)
@@ -184,7 +204,7 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
     a->do_integrate = integrate ? 1 : 0;
     a->log_mode = p->log_mode;
     a->max_steps = p->max_time_steps;
-    a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds, h->d_thr2, h->d_clipcnt};
+    a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds, h->d_thr2, h->d_clipcnt, h->d_logtab};
     a->dt = p->dt;
     a->q = 2 * p->dt;                        // drone_env.py:269
     a->b = p->collision_weight * p->dt;      // drone_env.py:270
@@ -230,11 +250,35 @@ int launch_step(ds_handle *h, const ds::StepArgs &a, cudaStream_t st)
     else { DS_DISPATCH_NT(step_kernel, float, a, gm) }
 }
 
+#ifdef DS_FAST_BUILD   /* tuning builds: k = 2 and the generic k only */
+#define DS_DISPATCH_RO_K(REAL, NT, NB, ARGS, GEOM)                                        \
+    switch (h->k) {                                                                      \
+    case 2: return launch(ds::rollout_kernel<REAL, 2, NT, NB>, ARGS, GEOM, st);          \
+    default: return launch(ds::rollout_kernel<REAL, -1, NT, NB>, ARGS, GEOM, st);        \
+    }
+#else
+#define DS_DISPATCH_RO_K(REAL, NT, NB, ARGS, GEOM)                                        \
+    switch (h->k) {                                                                      \
+    case 0: return launch(ds::rollout_kernel<REAL, 0, NT, NB>, ARGS, GEOM, st);          \
+    case 1: return launch(ds::rollout_kernel<REAL, 1, NT, NB>, ARGS, GEOM, st);          \
+    case 2: return launch(ds::rollout_kernel<REAL, 2, NT, NB>, ARGS, GEOM, st);          \
+    case 3: return launch(ds::rollout_kernel<REAL, 3, NT, NB>, ARGS, GEOM, st);          \
+    case 4: return launch(ds::rollout_kernel<REAL, 4, NT, NB>, ARGS, GEOM, st);          \
+    default: return launch(ds::rollout_kernel<REAL, -1, NT, NB>, ARGS, GEOM, st);        \
+    }
+#endif
+
+#define DS_DISPATCH_RO(REAL, ARGS, GEOM)                                                  \
+    if (h->nt == 1024) { DS_DISPATCH_RO_K(REAL, 1024, 0, ARGS, GEOM) }                    \
+    else if (h->ro_NB == 1) { DS_DISPATCH_RO_K(REAL, 256, 1, ARGS, GEOM) }                \
+    else if (h->ro_NB == 4) { DS_DISPATCH_RO_K(REAL, 256, 4, ARGS, GEOM) }                \
+    else { DS_DISPATCH_RO_K(REAL, 256, 0, ARGS, GEOM) }
+
 int launch_rollout(ds_handle *h, const ds::RolloutArgs &a, cudaStream_t st)
 {
     const Geom gm{h->ro_blocks, h->ro_threads, h->ro_smem};
-    if (h->real_bytes == 8) { DS_DISPATCH_NT(rollout_kernel, double, a, gm) }
-    else { DS_DISPATCH_NT(rollout_kernel, float, a, gm) }
+    if (h->real_bytes == 8) { DS_DISPATCH_RO(double, a, gm) }
+    else { DS_DISPATCH_RO(float, a, gm) }
 }
 
 void free_slots(ds_handle *h)
@@ -314,7 +358,7 @@ int ds_create(const ds_config *cfg, ds_handle **out)
     h->simplify = cfg->simplify_zstate ? 1 : 0;
     h->real_bytes = cfg->real_bytes; h->device = cfg->device;
     h->d_xF = h->d_ds = h->d_delta = h->d_radius = h->d_logds = h->d_thr2 = nullptr;
-    h->d_clipcnt = nullptr;
+    h->d_clipcnt = nullptr; h->d_logtab = nullptr;
     h->act_stage = nullptr; h->act_stage_bytes = 0;
     h->h_radius.assign(cfg->radius, cfg->radius + cfg->n_agents);
     cudaDeviceProp prop;
@@ -323,6 +367,7 @@ int ds_create(const ds_config *cfg, ds_handle **out)
         return fail(DS_ERR_CUDA, "ds_create: cudaGetDeviceProperties failed");
     }
     h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
     plan_launch(h);
     if (h->step_smem > (size_t)prop.sharedMemPerBlockOptin || h->ro_smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete h;
@@ -339,7 +384,8 @@ void ds_destroy(ds_handle *h)
     if (!h) return;
     DeviceGuard guard(h->device);
     cudaFree(h->d_xF); cudaFree(h->d_ds); cudaFree(h->d_delta); cudaFree(h->d_radius);
-    cudaFree(h->d_logds); cudaFree(h->d_thr2); cudaFree(h->d_clipcnt); cudaFree(h->act_stage);
+    cudaFree(h->d_logds); cudaFree(h->d_thr2); cudaFree(h->d_clipcnt); cudaFree(h->d_logtab);
+    cudaFree(h->act_stage);
     free_slots(h);
     cudaFree(h->d_agg); cudaFree(h->d_done); cudaFree(h->d_atable);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -380,7 +426,7 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_
     if ((ro->z_tr == nullptr) != (ro->Ni_tr == nullptr))
         return fail(DS_ERR_ARG, "ds_rollout: z_tr and Ni_tr must be given together");
     ra.s.G = h->ro_G;
-    ra.T = ro->T; ra.TC = h->ro_TC; ra.n_actions = ro->n_actions;
+    ra.T = ro->T; ra.TC = h->ro_TC; ra.n_actions = ro->n_actions; ra.L = h->ro_L;
     ra.actions = ro->actions; ra.aidx = ro->action_idx; ra.atable = ro->action_table;
     ra.pos_tr = ro->pos_tr; ra.vel_tr = ro->vel_tr; ra.r_tr = ro->reward_tr; ra.tr_tr = ro->true_reward_tr;
     ra.z_tr = ro->z_tr; ra.Ni_tr = ro->Ni_tr; ra.ncoll_tr = ro->ncoll_tr; ra.fin_tr = ro->finished_tr;

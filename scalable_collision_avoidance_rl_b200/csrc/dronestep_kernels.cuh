@@ -2,16 +2,15 @@
 //
 // Work item = one ROW of one FRAME: agent i of environment e at one time slice.
 // A CTA owns G whole environments and TC consecutive time slices of them
-// (G * n * TC <= blockDim.x items, one item per thread):
+// (G * n * TC <= blockDim.x rows, one row per thread):
 //
 //   * step_kernel     TC = 1: drones.step() / rewards() for E environments.
 //   * rollout_kernel  T fused steps walked in chunks of TC slices.  The
 //       integrator is a single integrator (x <- x + dt u, drone_env.py:78-79,235)
-//       and the actions of a rollout are given up front, so the thread of slice s
-//       re-integrates its own agent from the chunk's start position through the
-//       chunk's actions in shared memory (s+1 sequential, bit-exact additions).
-//       All TC frames of the chunk are then evaluated CONCURRENTLY: time becomes
-//       a parallel axis, which is what fills 148 SMs when E * n is only ~4e4.
+//       and the actions of a rollout are given up front, so the positions of all TC
+//       slices of a chunk are produced first (sequential, bit-exact additions) and
+//       the TC frames are then evaluated CONCURRENTLY: time becomes a parallel
+//       axis, which is what fills 148 SMs when E * n is only ~4e4.
 //       Early termination (drone_env.py:248-256) is resolved after the frames are
 //       evaluated and before anything is stored: results of slices behind a
 //       finishing slice are dropped, so the observable behaviour is exactly that
@@ -23,8 +22,14 @@
 //           provably clipped to d_safety (drone_env.py:318 min(.., d_safety[i]))
 //           contributes log(1) = 0, no collision, and a Delta-disk count that is a
 //           per-agent constant -- 6 instructions, no sqrt;
-//   pass 2  only the NEAR pairs (a bit mask per 32 agents) take the exact path:
-//           sqrt, clip, zero rule, division, log, collision test, k-nearest insert.
+//   pass 2  only the NEAR pairs take the exact path: sqrt, clip, zero rule,
+//           division, log, collision test, k-nearest insert.
+// In the rollout kernel the near pairs of all rows of the CTA are compacted into a
+// shared-memory work list (row-contiguous, ascending j) and evaluated by ALL
+// threads of the CTA, one pair per thread per round, so that the expensive part
+// (sqrt / div / log) is load balanced instead of paying for the row with the most
+// neighbours in every warp; each row then folds its own segment of results in
+// ascending j, the summation order of the reference (drone_env.py:282-283).
 // The k+1 nearest are kept in (distance, index) lexicographic order, which is the
 // stable argsort order (drone_env.py:338); clipped agents all tie at d_safety and
 // enter in index order.
@@ -40,6 +45,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDA_ARCH__)
 #define DS_DEVICE_CODE 1
@@ -103,7 +109,70 @@ DS_HD double sqrt_rn(double a)
     return sqrt(a);
 #endif
 }
-DS_HD double log_r(double a) { return log(a); }
+
+// ---- natural log of the barrier term (drone_env.py:331).  The reference calls np.log, whose
+// last bit is platform dependent; what the contract fixes is the VALUE to 1e-5.  log_r is a
+// table-driven fp64 log within 2 ulp of libm, or 2e-18 absolute where the two table terms cancel
+// (checked in tests/test_row_logic_host.py):
+//   x = 2^e * m,  m in [sqrt(1/2), sqrt(2));  the top 7 mantissa bits of m pick (rc, lc) with
+//   rc ~ 1/centre of the interval and lc = -log(rc) (computed in long double on the host);
+//   r = fma(m, rc, -1)  (|r| <= 2^-8, single rounding);  log x = e ln2 + lc + log1p(r),
+//   log1p by its Taylor series through r^7 (truncation 2^-67).  The interval that contains 1 has
+//   rc = 1, lc = 0, so results near log(1) = 0 keep full RELATIVE accuracy.
+// Anything that is not a positive normal number (0, denormal, negative, inf, NaN) takes libm's log.
+struct LogTabEntry { double rc, lc; };
+constexpr int kLogTabSize = 128;
+constexpr int kLogTabOffset = 0x3ff00000 - 0x3fe6a09e;   // high-word shift that centres m on 1
+
+DS_HD long long double_bits(double a)
+{
+#if DS_DEVICE_CODE
+    return __double_as_longlong(a);
+#else
+    long long b; memcpy(&b, &a, sizeof b); return b;
+#endif
+}
+DS_HD double bits_double(long long b)
+{
+#if DS_DEVICE_CODE
+    return __longlong_as_double(b);
+#else
+    double a; memcpy(&a, &b, sizeof a); return a;
+#endif
+}
+DS_HD double log_r(double x, const LogTabEntry *__restrict__ tab)
+{
+    const long long b = double_bits(x);
+    const int hi = (int)(b >> 32);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
+    const int hs = hi + kLogTabOffset;
+    const int e = (hs >> 20) - 1023;
+    const LogTabEntry t = tab[(hs >> 13) & (kLogTabSize - 1)];
+    const double m = bits_double(b - ((long long)e << 52));
+    const double r = fma_rn(m, t.rc, -1.0);
+    double p = fma_rn(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma_rn(r, p, 1.0 / 5.0);
+    p = fma_rn(r, p, -1.0 / 4.0);
+    p = fma_rn(r, p, 1.0 / 3.0);
+    p = fma_rn(r, p, -0.5);
+    const double sres = fma_rn(mul_rn(r, r), p, r);
+    return fma_rn((double)e, 0.6931471805599453094, add_rn(t.lc, sres));
+}
+// Host-side table fill (also used by tests/rowcheck): entry idx covers the doubles whose shifted
+// high word has mantissa field [idx << 13, (idx + 1) << 13).
+inline void fill_log_table(LogTabEntry *tab)
+{
+    for (int idx = 0; idx < kLogTabSize; ++idx) {
+        const long long a = (long long)(0x3ff00000 + (idx << 13) - kLogTabOffset) << 32;
+        double lo, hi;
+        const long long a2 = a + ((long long)0x2000 << 32);
+        memcpy(&lo, &a, sizeof lo); memcpy(&hi, &a2, sizeof hi);
+        if (lo <= 1.0 && 1.0 < hi) { tab[idx].rc = 1.0; tab[idx].lc = 0.0; continue; }
+        const double rc = 1.0 / (0.5 * (lo + hi));
+        tab[idx].rc = rc;
+        tab[idx].lc = (double)(-logl((long double)rc));
+    }
+}
 DS_HD float add_rn(float a, float b)
 {
 #if DS_DEVICE_CODE
@@ -152,7 +221,7 @@ DS_HD float sqrt_rn(float a)
     return sqrtf(a);
 #endif
 }
-DS_HD float log_r(float a) { return logf(a); }
+DS_HD float log_r(float a, const LogTabEntry *) { return logf(a); }
 
 DS_HD int lowest_bit(unsigned m)   // index of the lowest set bit, m != 0
 {
@@ -192,6 +261,7 @@ struct Consts {              // device arrays, length n (xF: 2n); Real typed unl
     const void *xF, *d_safety, *delta, *radius, *log_ds;
     const void *thr2;        // Real: pairs with |xi-xj|^2 >= thr2[i] are provably clipped to d_safety[i]
     const int *clipcnt;      // int: #{j != i : d_safety[i] <= delta[j]}  (Delta-disk count of clipped pairs)
+    const LogTabEntry *logtab;   // kLogTabSize entries (log_r)
 };
 
 struct StepArgs {
@@ -208,6 +278,7 @@ struct StepArgs {
 struct RolloutArgs {
     StepArgs s;
     int T, TC, n_actions;
+    int L;                   // capacity of the CTA's near-pair work list
     const void *actions;     // Real [T][E][n][2] or null
     const uint8_t *aidx;     // u8 [T][E][n]
     const void *atable;      // Real [n_actions][2]
@@ -247,6 +318,52 @@ DS_HD AgentConst<Real> load_agent_const(const Consts &c, int i)
     return a;
 }
 
+// ---------------------------------------------------------------- one pair (i, j), j != i
+// distance_data() for one entry of the pair matrix (drone_env.py:314-332).  A pair whose d_ij is
+// exactly d_safety[i] is CLIPPED: d_ij_norm = 1, log = 0, no collision -- logd stays 0.
+template <typename Real> struct PairOut {
+    Real d, logd;
+    bool in_disk, coll;
+};
+
+template <typename Real>
+DS_HD void eval_pair(PairOut<Real> &po, Real xi, Real yi, Real xj, Real yj, Real ds_i, Real rad_i,
+                     Real rad_j, Real delta_j, Real log_ds_i, const ParamsR<Real> &P,
+                     const LogTabEntry *__restrict__ tab)
+{
+    const Real dx = sub_rn(xi, xj), dy = sub_rn(yi, yj);
+    const Real dist = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));     // :318 (BLAS ddot)
+    const Real raw = sub_rn(sub_rn(dist, rad_i), rad_j);           // :318
+    Real d = (ds_i < raw) ? ds_i : raw;                            // python min(raw, d_safety[i])
+    if (d == (Real)0) d = P.zero_eps;                              // :319-320
+    po.d = d;
+    po.in_disk = d <= delta_j;                                     // :328 deltas[j]
+    po.logd = (Real)0;
+    po.coll = false;
+    if (d != ds_i) {
+        // not clipped: d_ij_norm != 1, the barrier term is live (:321,327,330-332)
+        if (P.log_mode == 0) {
+            const Real dn = div_rn(ds_i, d);
+            po.coll = dn <= (Real)0;
+            po.logd = po.coll ? P.sentinel : log_r(dn, tab);
+        } else {
+            po.coll = (ds_i > (Real)0) ? (d < (Real)0) : (ds_i == (Real)0);
+            po.logd = po.coll ? P.sentinel : sub_rn(log_ds_i, log_r(fabs(d), tab));
+        }
+    }
+}
+
+// Near-pair work-list entry (rollout kernel).  Before evaluation: row | j << 10 | i << 20.
+// After evaluation the same word holds j and the flags of the pair; (d, logd) sit in a parallel
+// array.  adj = [in_disk] - [d_safety[i] <= delta[j]] + 1 corrects the Delta-disk count, which
+// starts from "every pair is clipped".
+constexpr unsigned kEntSkip = 0xffffffffu;                         // slot of a row that overflowed
+DS_HD unsigned pack_entry(int row, int j, int i) { return (unsigned)row | ((unsigned)j << 10) | ((unsigned)i << 20); }
+DS_HD unsigned pack_result(int j, bool in_disk, bool coll, int adj1)
+{
+    return (unsigned)j | (in_disk ? 1u << 10 : 0u) | (coll ? 1u << 11 : 0u) | ((unsigned)adj1 << 12);
+}
+
 // ---------------------------------------------------------------- one row of the pair matrix
 // Everything rewards() derives for agent i (drone_env.py:260-293) from the staged
 // positions of its frame.
@@ -283,29 +400,75 @@ DS_HD bool topk_offer(RowResult<Real, K> &o, int kk, Real d, int j)
     return true;
 }
 
+// Running state of a row while its pairs are folded in ascending j.
+template <typename Real> struct RowAcc {
+    Real sum_local, sum_all;   // :282, :283
+    int ncoll, cnt_nd;
+    bool self_unclipped;
+};
+
+// j == i (:323-325): dist = 0, d_ii = min(-2 l_i, d_safety[i]), d_norm = 1 -> no barrier term.
+template <typename Real, int K>
+DS_HD void row_begin(RowResult<Real, K> &o, RowAcc<Real> &acc, int kk, int i, const AgentConst<Real> &c)
+{
+    constexpr int CAP = RowResult<Real, K>::CAP;
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) { o.td[m] = real_inf<Real>(); o.tj[m] = 0; }
+    acc.sum_local = 0; acc.sum_all = 0; acc.ncoll = 0;
+    const Real raw_ii = sub_rn(sub_rn((Real)0, c.radius), c.radius);
+    const Real d_ii = (c.ds < raw_ii) ? c.ds : raw_ii;
+    acc.cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);               // :328 deltas[j], j == i
+    acc.self_unclipped = (d_ii != c.ds);
+    if (d_ii < c.ds) topk_offer<Real, K>(o, kk, d_ii, i);
+}
+
+// Fold one evaluated near pair (ascending j: summation order of :282-283).  Returns true when the
+// pair is NOT clipped (d_ij != d_safety[i]).
+template <typename Real, int K>
+DS_HD bool row_fold(RowResult<Real, K> &o, RowAcc<Real> &acc, int kk, const AgentConst<Real> &c, int j,
+                    Real d, Real logd, bool in_disk, bool coll, int adj)
+{
+    acc.cnt_nd += adj;                                                  // replaces the clipped-pair count
+    if (d != c.ds) {
+        acc.ncoll += coll ? 1 : 0;
+        acc.sum_all = add_rn(acc.sum_all, logd);                                              // :283
+        acc.sum_local = add_rn(acc.sum_local, mul_rn(logd, in_disk ? (Real)1 : (Real)0));     // :282
+        if (d < c.ds) topk_offer<Real, K>(o, kk, d, j);
+        return true;
+    }
+    return false;
+}
+
+// Goal cost, rewards, Delta-disk count and termination flag of the row (:249-251,272-288,346).
+template <typename Real, int K>
+DS_HD void row_end(RowResult<Real, K> &o, const RowAcc<Real> &acc, Real xi, Real yi, const AgentConst<Real> &c,
+                   const ParamsR<Real> &P)
+{
+    const Real gx = sub_rn(c.xF, xi), gy = sub_rn(c.yF, yi);
+    const Real nrm = sqrt_rn(add_rn(mul_rn(gx, gx), mul_rn(gy, gy)));     // :249,276 (axis norm, unfused)
+    const Real goal = mul_rn(P.q, mul_rn(nrm, nrm));                      // :276
+    o.r = -nan_to_num(add_rn(goal, mul_rn(P.b, acc.sum_local)));          // :282,287
+    o.tr = -nan_to_num(add_rn(goal, mul_rn(P.b, acc.sum_all)));           // :283,288
+    o.zx = -gx; o.zy = -gy;                                               // :357
+    o.ncoll = acc.ncoll;
+    o.in_range = acc.cnt_nd - 1;                                          // :346
+    o.at_goal = nrm <= P.goal_tol;
+}
+
+// Whole row in one thread: both passes inline (step kernel; rollout rows whose near pairs did not
+// fit the CTA's work list).
 template <typename Real, int K>
 DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
                     const AgentConst<Real> &c,
                     const typename vec2_of<Real>::type *__restrict__ s_pos,
                     const Real *__restrict__ s_delta,
                     const Real *__restrict__ s_radius,
-                    const ParamsR<Real> &P)
+                    const ParamsR<Real> &P, const LogTabEntry *__restrict__ tab)
 {
     using V2 = typename vec2_of<Real>::type;
     const int kk = (K >= 0) ? K : P.k;
-    constexpr int CAP = RowResult<Real, K>::CAP;
-#pragma unroll
-    for (int m = 0; m < CAP; ++m) { o.td[m] = real_inf<Real>(); o.tj[m] = 0; }
-
-    Real sum_local = 0, sum_all = 0;
-    int ncoll = 0;
-    // j == i (:323-325): dist = 0, d_ii = min(-2 l_i, d_safety[i]), d_norm = 1 -> no barrier term
-    const Real raw_ii = sub_rn(sub_rn((Real)0, c.radius), c.radius);
-    const Real d_ii = (c.ds < raw_ii) ? c.ds : raw_ii;
-    int cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);               // :328 deltas[j], j == i
-    const bool self_unclipped = (d_ii != c.ds);
-    if (d_ii < c.ds) topk_offer<Real, K>(o, kk, d_ii, i);
-
+    RowAcc<Real> acc;
+    row_begin<Real, K>(o, acc, kk, i, c);
     for (int j0 = 0; j0 < n; j0 += 32) {
         const int jn = (n - j0 < 32) ? (n - j0) : 32;
         // pass 1: which agents of this block of 32 are NOT provably clipped
@@ -319,39 +482,19 @@ DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
         }
         const unsigned selfbit = ((unsigned)(i - j0) < 32u) ? (1u << (i - j0)) : 0u;
         near &= ~selfbit;
-        unsigned unclipped = self_unclipped ? selfbit : 0u;             // agents with d_ij != d_safety[i]
-        // pass 2: exact evaluation of the near pairs, ascending j (summation order of :282-283)
+        unsigned unclipped = acc.self_unclipped ? selfbit : 0u;         // agents with d_ij != d_safety[i]
+        // pass 2: exact evaluation of the near pairs, ascending j
         while (near) {
             const int jj = lowest_bit(near);
             near &= near - 1;
             const int j = j0 + jj;
             const V2 pj = s_pos[j];
-            const Real dx = sub_rn(xi, pj.x), dy = sub_rn(yi, pj.y);
-            const Real dist = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));     // :318 (BLAS ddot)
-            const Real raw = sub_rn(sub_rn(dist, c.radius), s_radius[j]);   // :318
-            Real d = (c.ds < raw) ? c.ds : raw;                             // python min(raw, d_safety[i])
-            if (d == (Real)0) d = P.zero_eps;                               // :319-320
             const Real dl = s_delta[j];
-            const bool in_disk = d <= dl;                                   // :328 deltas[j]
-            cnt_nd += (in_disk ? 1 : 0) - ((c.ds <= dl) ? 1 : 0);           // replaces the clipped-pair count
-            if (d != c.ds) {
-                // not clipped: d_ij_norm != 1, the barrier term is live (:321,327,330-332)
+            PairOut<Real> po;
+            eval_pair<Real>(po, xi, yi, pj.x, pj.y, c.ds, c.radius, s_radius[j], dl, c.log_ds, P, tab);
+            const int adj = (po.in_disk ? 1 : 0) - ((c.ds <= dl) ? 1 : 0);
+            if (row_fold<Real, K>(o, acc, kk, c, j, po.d, po.logd, po.in_disk, po.coll, adj))
                 unclipped |= 1u << jj;
-                Real logd;
-                bool coll;
-                if (P.log_mode == 0) {
-                    const Real dn = div_rn(c.ds, d);
-                    coll = dn <= (Real)0;
-                    logd = coll ? P.sentinel : log_r(dn);
-                } else {
-                    coll = (c.ds > (Real)0) ? (d < (Real)0) : (c.ds == (Real)0);
-                    logd = coll ? P.sentinel : sub_rn(c.log_ds, log_r(fabs(d)));
-                }
-                ncoll += coll ? 1 : 0;
-                sum_all = add_rn(sum_all, logd);                                                 // :283
-                sum_local = add_rn(sum_local, mul_rn(logd, in_disk ? (Real)1 : (Real)0));        // :282
-                if (d < c.ds) topk_offer<Real, K>(o, kk, d, j);
-            }
         }
         // clipped agents tie at exactly d_safety[i]: offered in index order until one is refused
         unsigned cm = ((jn == 32) ? 0xffffffffu : ((1u << jn) - 1u)) & ~unclipped;
@@ -361,15 +504,45 @@ DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
             cm &= cm - 1;
         }
     }
-    const Real gx = sub_rn(c.xF, xi), gy = sub_rn(c.yF, yi);
-    const Real nrm = sqrt_rn(add_rn(mul_rn(gx, gx), mul_rn(gy, gy)));     // :249,276 (axis norm, unfused)
-    const Real goal = mul_rn(P.q, mul_rn(nrm, nrm));                      // :276
-    o.r = -nan_to_num(add_rn(goal, mul_rn(P.b, sum_local)));              // :282,287
-    o.tr = -nan_to_num(add_rn(goal, mul_rn(P.b, sum_all)));               // :283,288
-    o.zx = -gx; o.zy = -gy;                                               // :357
-    o.ncoll = ncoll;
-    o.in_range = cnt_nd - 1;                                              // :346
-    o.at_goal = nrm <= P.goal_tol;
+    row_end<Real, K>(o, acc, xi, yi, c, P);
+}
+
+// The same row from its segment of the evaluated work list (rollout kernel): ent[q] / res[q],
+// q < cnt, ascending j.
+template <typename Real, int K>
+DS_HD void eval_row_from_list(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
+                              const AgentConst<Real> &c, const unsigned *__restrict__ ent,
+                              const typename vec2_of<Real>::type *__restrict__ res, int cnt,
+                              const ParamsR<Real> &P)
+{
+    using V2 = typename vec2_of<Real>::type;
+    const int kk = (K >= 0) ? K : P.k;
+    RowAcc<Real> acc;
+    row_begin<Real, K>(o, acc, kk, i, c);
+    unsigned unclipped_lo = (acc.self_unclipped && i < 32) ? (1u << i) : 0u;   // agents j < 32 only
+    for (int q = 0; q < cnt; ++q) {
+        const unsigned w = ent[q];
+        const V2 dv = res[q];
+        const int j = (int)(w & 1023u);
+        if (row_fold<Real, K>(o, acc, kk, c, j, dv.x, dv.y, (w >> 10) & 1u, (w >> 11) & 1u,
+                              (int)((w >> 12) & 3u) - 1))
+            if (j < 32) unclipped_lo |= 1u << j;
+    }
+    // clipped agents tie at exactly d_safety[i]: offered in index order until one is refused
+    // (a refusal is final: later real candidates can only push entries out)
+    for (int cj = 0; cj < n; ++cj) {
+        bool unclipped;
+        if (cj < 32) {
+            unclipped = (unclipped_lo >> cj) & 1u;
+        } else {
+            unclipped = (cj == i) && acc.self_unclipped;
+            for (int q = 0; q < cnt; ++q)
+                if ((int)(ent[q] & 1023u) == cj && res[q].x != c.ds) unclipped = true;
+        }
+        if (unclipped) continue;
+        if (!topk_offer<Real, K>(o, kk, c.ds, cj)) break;
+    }
+    row_end<Real, K>(o, acc, xi, yi, c, P);
 }
 
 // Write z_i (k+1 rows) and Ni_i (drone_env.py:344-397) for global agent index g.
@@ -524,7 +697,7 @@ step_kernel(const StepArgs a)
     __syncthreads();
     if (active) {
         RowResult<Real, K> o;
-        eval_row<Real, K>(o, n, i, xi, yi, c, sm.pos + le * n, sm.delta, sm.radius, P);
+        eval_row<Real, K>(o, n, i, xi, yi, c, sm.pos + le * n, sm.delta, sm.radius, P, a.c.logtab);
         reinterpret_cast<Real *>(a.r)[g] = o.r;
         reinterpret_cast<Real *>(a.tr)[g] = o.tr;
         write_obs<Real, K>(o, i, xi, yi, c, sm.pos + le * n, sm.act + le * n, sm.radius, P,
@@ -544,25 +717,89 @@ step_kernel(const StepArgs a)
 }
 
 // ---------------------------------------------------------------- rollout kernel
+// Shared memory of a rollout CTA.  Per CTA: constants [n], log table, work list [L].  Per row
+// (I = TC*G*n): action, position, r, true_r.  Per agent of a slice (A = G*n): chunk start
+// position, last executed velocity.  Per frame (F = TC*G): collision count, not-at-goal flag,
+// frame info, per-frame means.  Per environment (G): alive, t, executed slices.
+template <typename Real> struct RoSmem {
+    using V2 = typename vec2_of<Real>::type;
+    Real *delta, *radius, *dsafe, *logds;
+    LogTabEntry *logtab;
+    V2 *act, *pos, *p0, *vfin, *res;
+    Real *r, *tr;
+    unsigned *ent;
+    double *mr, *mtr;
+    int *cnt, *notgoal, *finfo, *alive, *tenv, *nexec, *lcount;
+    __host__ __device__ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+    __host__ __device__ static size_t bytes(int n, int G, int TC, int L)
+    {
+        const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
+        return align16(4 * n * sizeof(Real)) + kLogTabSize * sizeof(LogTabEntry) +
+               (2 * I + 2 * A + (size_t)L) * sizeof(V2) + align16(2 * I * sizeof(Real)) +
+               align16((size_t)L * sizeof(unsigned)) + 2 * F * sizeof(double) +
+               align16(3 * F * sizeof(int)) + align16((3 * (size_t)G + 1) * sizeof(int));
+    }
+    __device__ RoSmem(unsigned char *base, int n, int G, int TC, int L)
+    {
+        const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
+        unsigned char *p = base;
+        delta = reinterpret_cast<Real *>(p); radius = delta + n; dsafe = radius + n; logds = dsafe + n;
+        p += align16(4 * n * sizeof(Real));
+        logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);
+        act = reinterpret_cast<V2 *>(p); pos = act + I; p0 = pos + I; vfin = p0 + A; res = vfin + A;
+        p += (2 * I + 2 * A + (size_t)L) * sizeof(V2);
+        r = reinterpret_cast<Real *>(p); tr = r + I; p += align16(2 * I * sizeof(Real));
+        ent = reinterpret_cast<unsigned *>(p); p += align16((size_t)L * sizeof(unsigned));
+        mr = reinterpret_cast<double *>(p); mtr = mr + F; p += 2 * F * sizeof(double);
+        cnt = reinterpret_cast<int *>(p); notgoal = cnt + F; finfo = notgoal + F; p += align16(3 * F * sizeof(int));
+        alive = reinterpret_cast<int *>(p); tenv = alive + G; nexec = tenv + G; lcount = nexec + G;
+    }
+};
+
+// frame info word written by the frame's leader thread after the rows are evaluated
+#ifndef DS_RO_MINB
+#define DS_RO_MINB 2      // CTAs of 256 threads per SM the rollout kernel is compiled for (register cap)
+#endif
+constexpr int kFrameExec = 1, kFrameFin = 2, kFrameLast = 4;
+
 // T fused steps, TC time slices per chunk evaluated concurrently (see the header comment).
-template <typename Real, int K, int NT>
-__global__ void __launch_bounds__(NT, (NT <= 256) ? 2 : 1)
+// NB = number of 32-agent blocks whose near masks a row keeps in registers (n <= 32 NB);
+// NB == 0: any n, masks in local memory.
+//
+// One chunk:
+//   (a) actions of the chunk -> smem                                             | barrier
+//   (b) threads < A integrate their agent through the chunk's slices -> pos[]    | barrier
+//   (c) every row: pass 1 over its frame -> near masks; a warp scan + one smem atomic per
+//       warp gives the row a contiguous segment of the work list; entries written | barrier
+//   (d) all threads: one near pair per thread per round (eval_pair)              | barrier
+//   (e) every row folds its segment, finishes the row, posts r / true_r / collision count /
+//       not-at-goal to its frame                                                 | barrier
+//   (f) threads < F: leader of one frame each -- executed?, finished?, frame means   | barrier
+//   (g) every executed row stores its outputs; threads < G accumulate the episode sums.
+template <typename Real, int K, int NT, int NB>
+__global__ void __launch_bounds__(NT, (NT <= 256) ? DS_RO_MINB : 1)
 rollout_kernel(const RolloutArgs ra)
 {
     using V2 = typename vec2_of<Real>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const StepArgs &a = ra.s;
-    const int n = a.n, G = a.G, TC = ra.TC, E = a.E, T = ra.T;
-    CtaSmem<Real> sm(smem_raw, n, G, TC);
+    const int n = a.n, G = a.G, TC = ra.TC, E = a.E, T = ra.T, L = ra.L;
+    RoSmem<Real> sm(smem_raw, n, G, TC, L);
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
         sm.delta[idx] = ((const Real *)a.c.delta)[idx];
         sm.radius[idx] = ((const Real *)a.c.radius)[idx];
+        sm.dsafe[idx] = ((const Real *)a.c.d_safety)[idx];
+        sm.logds[idx] = ((const Real *)a.c.log_ds)[idx];
     }
+    if (sizeof(Real) == 8)
+        for (int idx = threadIdx.x; idx < kLogTabSize; idx += blockDim.x) sm.logtab[idx] = a.c.logtab[idx];
     const ParamsR<Real> P(a);
     const int kk = (K >= 0) ? K : a.k;
     const int cols = a.simplify ? 2 : 5;
     const int A = G * n;                              // agents per slice in this CTA
+    const int F = G * TC;                             // frames per chunk in this CTA
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const int s = tid / A, ag = tid - s * A;          // time slice within the chunk, agent slot
     const int le = ag / n, i = ag - le * n;
     const long long e = (long long)blockIdx.x * G + le;
@@ -579,11 +816,12 @@ rollout_kernel(const RolloutArgs ra)
         sm.vfin[ag] = reinterpret_cast<const V2 *>(a.vel)[g];
         if (i == 0) { sm.alive[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv[le] = a.t[e]; sm.nexec[le] = 0; }
     }
-    // per-environment episode accumulators live in one thread (s == 0, i == 0)
-    const bool acc_thread = active && s == 0 && i == 0;
+    // per-environment episode accumulators live in thread le (< G)
+    const long long e_acc = (long long)blockIdx.x * G + tid;
+    const bool acc_thread = tid < G && e_acc < E;
     double acc_r = 0, acc_tr = 0, acc_c = 0, acc_s = 0;
     if (acc_thread) {
-        const double *ag4 = ra.agg + (size_t)e * 4;
+        const double *ag4 = ra.agg + (size_t)e_acc * 4;
         acc_r = ag4[0]; acc_tr = ag4[1]; acc_c = ag4[2]; acc_s = ag4[3];
     }
     bool stepped = false;
@@ -601,53 +839,161 @@ rollout_kernel(const RolloutArgs ra)
         const bool in_chunk = active && s < nsl;
         const V2 u = u_next;
         if (active && t0 + TC + s < T) u_next = load_action(t0 + TC + s);   // prefetch the next chunk
+        // (a)
         if (in_chunk) sm.act[tid] = u;
-        __syncthreads();                                     // (1) actions, p0, alive, tenv visible
-        // episode accumulators of the PREVIOUS chunk, in time order (train_problem.py:98-100)
-        if (acc_thread) {
-            const int ne = sm.nexec[le];
-            for (int q = 0; q < ne; ++q) {
-                acc_r += sm.mr[q * G + le]; acc_tr += sm.mtr[q * G + le];
-                acc_c += (double)sm.mc[q * G + le]; acc_s += 1;
-            }
-            if (ne) stepped = true;
-            sm.nexec[le] = 0;
-        }
-        const bool valid = in_chunk && sm.alive[le] != 0;
-        const int tt0 = active ? sm.tenv[le] : 0;
-        V2 p{};
-        if (valid) {
-            p = sm.p0[ag];
-            for (int q = 0; q <= s; ++q) {                   // s+1 sequential single-integrator steps
-                const V2 uq = sm.act[q * A + ag];
-                p.x = add_rn(p.x, mul_rn(P.dt, uq.x));      // A = I, B = dt I (:78-79,235)
+        if (tid == 0) *sm.lcount = 0;
+        __syncthreads();
+        // (b) sequential single-integrator steps, one thread per agent (A = I, B = dt I, :78-79,235)
+        if (tid < A && e < E && sm.alive[le] != 0) {
+            V2 p = sm.p0[tid];
+            for (int q = 0; q < nsl; ++q) {
+                const V2 uq = sm.act[q * A + tid];
+                p.x = add_rn(p.x, mul_rn(P.dt, uq.x));
                 p.y = add_rn(p.y, mul_rn(P.dt, uq.y));
+                sm.pos[q * A + tid] = p;
             }
-            sm.pos[tid] = p;
-            if (i == 0) { sm.cnt[fr] = 0; sm.notgoal[fr] = 0; }
         }
-        __syncthreads();                                     // (2) positions of every frame staged
+        __syncthreads();
+        // (c) pass 1
+        const bool valid = in_chunk && sm.alive[le] != 0;
+        V2 p{};
+        constexpr int NBR = (NB > 0) ? NB : 32;
+        unsigned near[NBR];
+        int ncnt = 0;
+        const V2 *fpos = sm.pos + s * A + le * n;            // positions of this row's frame
+        if (valid) {
+            p = sm.pos[tid];
+            if (i == 0) { sm.cnt[fr] = 0; sm.notgoal[fr] = 0; }
+            if (NB > 0) {
+#pragma unroll
+                for (int bk = 0; bk < NBR; ++bk) {
+                    const int j0 = bk * 32;
+                    unsigned m = 0;
+                    if (j0 < n) {
+                        const int jn = (n - j0 < 32) ? (n - j0) : 32;
+#pragma unroll 4
+                        for (int jj = 0; jj < jn; ++jj) {
+                            const V2 pj = fpos[j0 + jj];
+                            const Real dx = sub_rn(p.x, pj.x), dy = sub_rn(p.y, pj.y);
+                            const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
+                            m |= ((d2 >= c.thr2) ? 0u : 1u) << jj;          // NaN -> near (exact path)
+                        }
+                        if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
+                    }
+                    near[bk] = m;
+                    ncnt += __popc(m);
+                }
+            } else {
+                for (int j0 = 0, bk = 0; j0 < n; j0 += 32, ++bk) {
+                    const int jn = (n - j0 < 32) ? (n - j0) : 32;
+                    unsigned m = 0;
+#pragma unroll 4
+                    for (int jj = 0; jj < jn; ++jj) {
+                        const V2 pj = fpos[j0 + jj];
+                        const Real dx = sub_rn(p.x, pj.x), dy = sub_rn(p.y, pj.y);
+                        const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
+                        m |= ((d2 >= c.thr2) ? 0u : 1u) << jj;
+                    }
+                    if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
+                    near[bk] = m;
+                    ncnt += __popc(m);
+                }
+            }
+        }
+        // segment of the work list: exclusive scan over the warp, one atomic per warp
+        int incl = ncnt;
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, w);
+            if (lane >= w) incl += v;
+        }
+        int wbase = 0;
+        if (lane == 31 && incl > 0) wbase = atomicAdd(sm.lcount, incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        const int seg = wbase + incl - ncnt;
+        const bool listed = ncnt == 0 || seg + ncnt <= L;    // otherwise the row evaluates itself in (e)
+        if (valid && ncnt > 0) {
+            int q = seg;
+            if (listed) {
+                const int nb = (NB > 0) ? NBR : (n + 31) / 32;
+#pragma unroll
+                for (int bk = 0; bk < nb; ++bk) {
+                    unsigned m = near[bk];
+                    while (m) {
+                        const int jj = lowest_bit(m);
+                        m &= m - 1;
+                        sm.ent[q++] = pack_entry(tid, bk * 32 + jj, i);
+                    }
+                }
+            } else {
+                for (; q < L && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
+            }
+        }
+        __syncthreads();
+        // (d) pass 2: one near pair per thread per round
+        {
+            const int M = (*sm.lcount < L) ? *sm.lcount : L;
+            for (int q = tid; q < M; q += blockDim.x) {
+                const unsigned w = sm.ent[q];
+                if (w == kEntSkip) continue;
+                const int row = (int)(w & 1023u), j = (int)((w >> 10) & 1023u), ri = (int)(w >> 20);
+                const V2 pi = sm.pos[row], pj = sm.pos[row - ri + j];
+                const Real ds_i = sm.dsafe[ri], dl = sm.delta[j];
+                PairOut<Real> po;
+                eval_pair<Real>(po, pi.x, pi.y, pj.x, pj.y, ds_i, sm.radius[ri], sm.radius[j], dl, sm.logds[ri], P,
+                                sm.logtab);
+                V2 dv; dv.x = po.d; dv.y = po.logd;
+                sm.res[q] = dv;
+                sm.ent[q] = pack_result(j, po.in_disk, po.coll, (po.in_disk ? 1 : 0) - ((ds_i <= dl) ? 1 : 0) + 1);
+            }
+        }
+        __syncthreads();
+        // (e) rows
         RowResult<Real, K> o;
         if (valid) {
-            eval_row<Real, K>(o, n, i, p.x, p.y, c, sm.pos + s * A + le * n, sm.delta, sm.radius, P);
+            if (listed)
+                eval_row_from_list<Real, K>(o, n, i, p.x, p.y, c, sm.ent + seg, sm.res + seg, ncnt, P);
+            else
+                eval_row<Real, K>(o, n, i, p.x, p.y, c, fpos, sm.delta, sm.radius, P, sm.logtab);
             sm.r[tid] = o.r;
             sm.tr[tid] = o.tr;
             if (o.ncoll) atomicAdd(&sm.cnt[fr], o.ncoll);
             if (!o.at_goal) sm.notgoal[fr] = 1;
         }
-        __syncthreads();                                     // (3) per-frame reductions complete
+        __syncthreads();
+        // (f) frame leaders: a slice executes iff no earlier slice of this chunk finished the
+        // episode (:248-256); frame means for the episode sums (train_problem.py:98-100)
+        if (tid < F) {
+            const int fs = tid / G, fle = tid - fs * G;      // slice, local environment of frame tid
+            const long long fe_ = (long long)blockIdx.x * G + fle;
+            int info = 0;
+            if (fe_ < E && fs < nsl && sm.alive[fle] != 0) {
+                const int ft0 = sm.tenv[fle];
+                bool exec = true;
+                for (int q = 0; q < fs; ++q)
+                    if (sm.notgoal[q * G + fle] == 0 || ft0 + q >= a.max_steps - 1) exec = false;
+                if (exec) {
+                    const bool fin = (sm.notgoal[tid] == 0) || (ft0 + fs >= a.max_steps - 1);
+                    const bool last = fin || (fs == nsl - 1);        // last executed slice of this chunk
+                    info = kFrameExec | (fin ? kFrameFin : 0) | (last ? kFrameLast : 0);
+                    double sr = 0, st = 0;
+                    const Real *rr = sm.r + fs * A + fle * n, *rt = sm.tr + fs * A + fle * n;
+                    for (int j = 0; j < n; ++j) { sr += (double)rr[j]; st += (double)rt[j]; }
+                    sm.mr[tid] = sr / n; sm.mtr[tid] = st / n;
+                }
+            }
+            sm.finfo[tid] = info;
+        }
+        __syncthreads();
+        // (g) stores
         const size_t at = (size_t)(t0 + s) * EN + g;
         const size_t fe = (size_t)(t0 + s) * E + (size_t)e;
         if (valid) {
-            // a slice executes iff no earlier slice of this chunk finished the episode (:248-256)
-            bool exec = true;
-            for (int q = 0; q < s; ++q)
-                if (sm.notgoal[q * G + le] == 0 || tt0 + q >= a.max_steps - 1) exec = false;
-            if (exec) {
+            const int info = sm.finfo[fr];
+            if (info & kFrameExec) {
                 const int nc = sm.cnt[fr];
-                const bool fin = (sm.notgoal[fr] == 0) || (tt0 + s >= a.max_steps - 1);
-                const bool last = fin || (s == nsl - 1);     // last executed slice of this chunk
-                const V2 *fpos = sm.pos + s * A + le * n, *fvel = sm.act + s * A + le * n;
+                const bool fin = (info & kFrameFin) != 0, last = (info & kFrameLast) != 0;
+                const V2 *fvel = sm.act + s * A + le * n;
                 if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
                 if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = u;              // :238
                 if (ra.r_tr) reinterpret_cast<Real *>(ra.r_tr)[at] = o.r;
@@ -668,10 +1014,6 @@ rollout_kernel(const RolloutArgs ra)
                 if (i == 0) {
                     if (ra.ncoll_tr) ra.ncoll_tr[fe] = nc;
                     if (ra.fin_tr) ra.fin_tr[fe] = fin ? 1 : 0;
-                    double sr = 0, st = 0;
-                    for (int j = 0; j < n; ++j) { sr += (double)sm.r[s * A + le * n + j]; st += (double)sm.tr[s * A + le * n + j]; }
-                    sm.mr[fr] = sr / n; sm.mtr[fr] = st / n; sm.mc[fr] = nc;
-                    if (last) { sm.nexec[le] = s + 1; sm.tenv[le] = tt0 + s + 1; if (fin) sm.alive[le] = 0; }
                 }
             } else if (i == 0 && ra.fin_tr) {
                 ra.fin_tr[fe] = 2;
@@ -679,24 +1021,39 @@ rollout_kernel(const RolloutArgs ra)
         } else if (in_chunk && i == 0 && ra.fin_tr) {
             ra.fin_tr[fe] = 2;
         }
+        // episode sums of this chunk, in time order; environment bookkeeping for the next chunk
+        // (alive / tenv are read again only after the next chunk's first barrier)
+        if (acc_thread && sm.alive[tid] != 0) {
+            int ne = 0;
+            for (int q = 0; q < nsl; ++q) {
+                const int info = sm.finfo[q * G + tid];
+                if (!(info & kFrameExec)) break;
+                acc_r += sm.mr[q * G + tid]; acc_tr += sm.mtr[q * G + tid];
+                acc_c += (double)sm.cnt[q * G + tid]; acc_s += 1;
+                ++ne;
+            }
+            if (ne) stepped = true;
+            sm.nexec[tid] = ne;
+        }
+        __syncthreads();
+        if (acc_thread && sm.alive[tid] != 0) {
+            // after the barrier: every row of this chunk has read alive / tenv
+            const int ne = sm.nexec[tid];
+            sm.tenv[tid] += ne;
+            if (ne > 0 && (sm.finfo[(ne - 1) * G + tid] & kFrameFin)) sm.alive[tid] = 0;
+        }
     }
     __syncthreads();
     if (active && s == 0) {
         reinterpret_cast<V2 *>(a.pos)[g] = sm.p0[ag];
         reinterpret_cast<V2 *>(a.vel)[g] = sm.vfin[ag];
-        if (i == 0) {
-            const int ne = sm.nexec[le];
-            for (int q = 0; q < ne; ++q) {
-                acc_r += sm.mr[q * G + le]; acc_tr += sm.mtr[q * G + le];
-                acc_c += (double)sm.mc[q * G + le]; acc_s += 1;
-            }
-            if (ne) stepped = true;
-            a.t[e] = sm.tenv[le];
-            if (stepped) {
-                if (sm.alive[le] == 0) ra.done[e] = 1;
-                double *ag4 = ra.agg + (size_t)e * 4;
-                ag4[0] = acc_r; ag4[1] = acc_tr; ag4[2] = acc_c; ag4[3] = acc_s;
-            }
+    }
+    if (acc_thread) {
+        a.t[e_acc] = sm.tenv[tid];
+        if (stepped) {
+            if (sm.alive[tid] == 0) ra.done[e_acc] = 1;
+            double *ag4 = ra.agg + (size_t)e_acc * 4;
+            ag4[0] = acc_r; ag4[1] = acc_tr; ag4[2] = acc_c; ag4[3] = acc_s;
         }
     }
 }

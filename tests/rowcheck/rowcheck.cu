@@ -1,13 +1,15 @@
-// TEST INFRASTRUCTURE ONLY -- runs the row logic of dronestep_kernels.cuh (eval_row + write_obs,
-// the __host__ __device__ part) on the CPU for one frame, so that the near/clipped split, the
-// Delta-disk count and the k-nearest selection can be checked against the oracle without a GPU.
+// TEST INFRASTRUCTURE ONLY -- runs the row logic of dronestep_kernels.cuh (eval_row / the work-list
+// path eval_pair + eval_row_from_list, write_obs: the __host__ __device__ part) on the CPU for one
+// frame, so that the near/clipped split, the Delta-disk count and the k-nearest selection can be
+// checked against the oracle without a GPU.  path = 0: whole row in one call (step kernel);
+// path = 1: near pairs through a work list exactly as the rollout kernel lays them out.
 // Never linked into libdronestep.so; the product has no CPU path.
 #include "../../scalable_collision_avoidance_rl_b200/csrc/dronestep_kernels.cuh"
 #include <vector>
 #include <cmath>
 
 template <typename Real, int K>
-static void run(int n, int k, int simplify, int log_mode, const double *pos, const double *vel,
+static void run(int path, int n, int k, int simplify, int log_mode, const double *pos, const double *vel,
                 const double *xF, const double *dsf, const double *delta, const double *radius,
                 double collision_weight, double *r, double *tr, double *z, int *Ni, int *ncoll, int *notgoal)
 {
@@ -39,7 +41,9 @@ static void run(int n, int k, int simplify, int log_mode, const double *pos, con
     a.n = n; a.k = k; a.simplify = simplify; a.log_mode = log_mode;
     a.dt = 0.05; a.q = 2 * 0.05; a.b = collision_weight * 0.05; a.goal_tol = 0.2; a.sentinel = 9.99E3;
     a.zero_eps = -1e-6; a.ghost = 1.1;
-    a.c = ds::Consts{cxF.data(), cds.data(), cdl.data(), crd.data(), clg.data(), cthr.data(), clip.data()};
+    std::vector<ds::LogTabEntry> tab(ds::kLogTabSize);
+    ds::fill_log_table(tab.data());
+    a.c = ds::Consts{cxF.data(), cds.data(), cdl.data(), crd.data(), clg.data(), cthr.data(), clip.data(), tab.data()};
     const ds::ParamsR<Real> P(a);
     const int cols = simplify ? 2 : 5;
     std::vector<Real> zr((size_t)n * (k + 1) * cols);
@@ -47,19 +51,49 @@ static void run(int n, int k, int simplify, int log_mode, const double *pos, con
     for (int i = 0; i < n; ++i) {
         const ds::AgentConst<Real> c = ds::load_agent_const<Real>(a.c, i);
         ds::RowResult<Real, K> o;
-        ds::eval_row<Real, K>(o, n, i, sp[i].x, sp[i].y, c, sp.data(), cdl.data(), crd.data(), P);
+        if (path == 0) {
+            ds::eval_row<Real, K>(o, n, i, sp[i].x, sp[i].y, c, sp.data(), cdl.data(), crd.data(), P, tab.data());
+        } else {
+            // rollout kernel phases (c) -> (d) -> (e) for this row
+            std::vector<unsigned> ent;
+            std::vector<V2> res;
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const Real dx = sp[i].x - sp[j].x, dy = sp[i].y - sp[j].y;
+                const Real d2 = ds::fma_rn(dy, dy, dx * dx);
+                if (!(d2 >= c.thr2)) ent.push_back(ds::pack_entry(i, j, i));
+            }
+            res.resize(ent.size());
+            for (size_t q = 0; q < ent.size(); ++q) {
+                const unsigned w = ent[q];
+                const int row = (int)(w & 1023u), j = (int)((w >> 10) & 1023u), ri = (int)(w >> 20);
+                ds::PairOut<Real> po;
+                ds::eval_pair<Real>(po, sp[row].x, sp[row].y, sp[row - ri + j].x, sp[row - ri + j].y, cds[ri], crd[ri],
+                                    crd[j], cdl[j], clg[ri], P, tab.data());
+                res[q].x = po.d; res[q].y = po.logd;
+                ent[q] = ds::pack_result(j, po.in_disk, po.coll, (po.in_disk ? 1 : 0) - ((cds[ri] <= cdl[j]) ? 1 : 0) + 1);
+            }
+            ds::eval_row_from_list<Real, K>(o, n, i, sp[i].x, sp[i].y, c, ent.data(), res.data(), (int)ent.size(), P);
+        }
         ds::write_obs<Real, K>(o, i, sp[i].x, sp[i].y, c, sp.data(), sv.data(), crd.data(), P, zr.data(), Ni, (size_t)i);
         r[i] = o.r; tr[i] = o.tr; *ncoll += o.ncoll; if (!o.at_goal) *notgoal = 1;
     }
     for (size_t q = 0; q < zr.size(); ++q) z[q] = zr[q];
 }
 
-extern "C" int rowcheck_frame(int real_bytes, int n, int k, int simplify, int log_mode, const double *pos,
+extern "C" double rowcheck_log(double x)
+{
+    static std::vector<ds::LogTabEntry> tab;
+    if (tab.empty()) { tab.resize(ds::kLogTabSize); ds::fill_log_table(tab.data()); }
+    return ds::log_r(x, tab.data());
+}
+
+extern "C" int rowcheck_frame(int path, int real_bytes, int n, int k, int simplify, int log_mode, const double *pos,
                               const double *vel, const double *xF, const double *dsf, const double *delta,
                               const double *radius, double collision_weight, double *r, double *tr, double *z,
                               int *Ni, int *ncoll, int *notgoal)
 {
-#define RUN(REAL, KK) run<REAL, KK>(n, k, simplify, log_mode, pos, vel, xF, dsf, delta, radius, collision_weight, r, tr, z, Ni, ncoll, notgoal)
+#define RUN(REAL, KK) run<REAL, KK>(path, n, k, simplify, log_mode, pos, vel, xF, dsf, delta, radius, collision_weight, r, tr, z, Ni, ncoll, notgoal)
     if (real_bytes == 8) { if (k == 2) RUN(double, 2); else RUN(double, -1); }
     else { if (k == 2) RUN(float, 2); else RUN(float, -1); }
     return 0;

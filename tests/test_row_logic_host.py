@@ -30,16 +30,18 @@ def rowlib():
                         "-fPIC,-ffp-contract=off", "-shared", "-o", OUT, SRC], check=True)
     lib = ctypes.CDLL(OUT)
     lib.rowcheck_frame.restype = ctypes.c_int
+    lib.rowcheck_log.restype = ctypes.c_double
+    lib.rowcheck_log.argtypes = [ctypes.c_double]
     return lib
 
 
-def _frame(lib, real_bytes, n, k, simplify, log_mode, pos, vel, xF, ds, dl, rad, cw):
+def _frame(lib, path, real_bytes, n, k, simplify, log_mode, pos, vel, xF, ds, dl, rad, cw):
     cols = 2 if simplify else 5
     r, tr = np.zeros(n), np.zeros(n)
     z = np.zeros((n, k + 1, cols)); Ni = np.full((n, k + 1), -1, np.int32)
     nc, ng = ctypes.c_int(0), ctypes.c_int(0)
     keep = [np.ascontiguousarray(x, np.float64) for x in (pos, vel, xF, ds, dl, rad)]
-    lib.rowcheck_frame(real_bytes, n, k, int(simplify), log_mode, *[x.ctypes.data_as(ctypes.c_void_p) for x in keep],
+    lib.rowcheck_frame(path, real_bytes, n, k, int(simplify), log_mode, *[x.ctypes.data_as(ctypes.c_void_p) for x in keep],
                        ctypes.c_double(cw), r.ctypes.data_as(ctypes.c_void_p),
                        tr.ctypes.data_as(ctypes.c_void_p), z.ctypes.data_as(ctypes.c_void_p),
                        Ni.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nc), ctypes.byref(ng))
@@ -63,9 +65,10 @@ CASES = [  # n, k, simplify, grid, delta, box, hetero_delta, hetero_radius
 ]
 
 
+@pytest.mark.parametrize("path", [0, 1], ids=["row", "worklist"])
 @pytest.mark.parametrize("log_mode", [0, 1])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c[0]}_k{c[1]}_{'s' if c[2] else 'f'}_box{c[5]}")
-def test_row_logic_matches_oracle(rowlib, case, log_mode):
+def test_row_logic_matches_oracle(rowlib, case, log_mode, path):
     n, k, simplify, grid, delta, box, hd, hr = case
     rng = np.random.default_rng(100 + n + k)
     rad = rng.uniform(0.05, 0.15, n) if hr else np.full(n, 0.1)
@@ -84,7 +87,7 @@ def test_row_logic_matches_oracle(rowlib, case, log_mode):
     orc.set_state(pos, vel)
     ref = orc.observe()
     for f in range(frames):
-        r, tr, z, Ni, nc, ng = _frame(rowlib, 8, n, k, simplify, log_mode, pos[f], vel[f], xF, ds, dl, rad, 0.35)
+        r, tr, z, Ni, nc, ng = _frame(rowlib, path, 8, n, k, simplify, log_mode, pos[f], vel[f], xF, ds, dl, rad, 0.35)
         assert_close(r, ref.r[f], FP64_TOL, f"r frame {f}")
         assert_close(tr, ref.true_r[f], FP64_TOL, f"true_r frame {f}")
         assert nc == ref.ncoll[f], f"ncoll frame {f}"
@@ -102,6 +105,32 @@ def test_row_logic_float32_close(rowlib):
     orc.set_state(pos)
     ref = orc.observe()
     for f in range(64):
-        r, tr, z, Ni, nc, ng = _frame(rowlib, 4, n, k, True, 0, pos[f], np.zeros((n, 2)), xF, ds, dl, rad, 0.2)
+        r, tr, z, Ni, nc, ng = _frame(rowlib, 1, 4, n, k, True, 0, pos[f], np.zeros((n, 2)), xF, ds, dl, rad, 0.2)
         err = np.abs(r - ref.r[f]) / np.maximum(1, np.abs(ref.r[f]))
         assert err.max() < 5e-6
+
+
+def test_table_log_accuracy(rowlib):
+    """log_r (dronestep_kernels.cuh) against libm over the positive normal range: within 2 ulp,
+    or within 2e-18 absolute where lc + log1p(r) cancels (results below ~1e-2 in the table
+    intervals next to the one that holds 1); exact special cases; log(1) = 0."""
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([
+        np.exp(rng.uniform(-700, 700, 200000)),              # whole exponent range
+        rng.uniform(0.5, 2.0, 200000),                       # the range the barrier term lives in
+        1.0 + rng.uniform(-1, 1, 100000) * 10.0 ** rng.uniform(-15, -2, 100000),
+        np.array([1.0, 2.0, 0.5, np.sqrt(2.0), np.sqrt(0.5), np.nextafter(1.0, 2), np.nextafter(1.0, 0),
+                  2.2250738585072014e-308, 1.7976931348623157e308, 1.19 / 0.3, 1.19 / 1.1899999]),
+    ])
+    got = np.array([rowlib.rowcheck_log(float(x)) for x in xs])
+    ref = np.log(xs)
+    ulp = np.spacing(np.abs(ref))
+    err = np.abs(got - ref) / np.maximum(2.0 * ulp, 2e-18)
+    assert err.max() <= 1.0, f"max error {np.abs(got - ref).max():.3e} at x = {xs[err.argmax()]!r}"
+    near1 = np.abs(xs - 1.0) < 1e-4                           # the rc = 1 interval: relative accuracy
+    assert (np.abs(got - ref)[near1] <= 2.0 * ulp[near1]).all()
+    assert rowlib.rowcheck_log(1.0) == 0.0
+    with np.errstate(all="ignore"):
+        assert rowlib.rowcheck_log(0.0) == -np.inf and np.isnan(rowlib.rowcheck_log(-1.0))
+        assert rowlib.rowcheck_log(np.inf) == np.inf and np.isnan(rowlib.rowcheck_log(np.nan))
+        assert abs(rowlib.rowcheck_log(5e-324) - np.log(5e-324)) < 1e-12
