@@ -7,6 +7,7 @@
 #include "../../include/dronestep.h"
 #include "dronestep_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -223,6 +224,8 @@ int launch(KernelT kernel, const ArgsT &args, const Geom &gm, cudaStream_t st)
 {
     if (gm.smem > 48 * 1024)
         DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
+    // residency is shared-memory bound for small CTAs: ask for the largest carve-out
+    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kernel<<<gm.blocks, gm.threads, gm.smem, st>>>(args);
     DS_CUDA(cudaGetLastError());
     return DS_OK;
@@ -426,14 +429,30 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_
     if ((ro->z_tr == nullptr) != (ro->Ni_tr == nullptr))
         return fail(DS_ERR_ARG, "ds_rollout: z_tr and Ni_tr must be given together");
     ra.s.G = h->ro_G;
-    ra.T = ro->T; ra.TC = h->ro_TC; ra.n_actions = ro->n_actions; ra.L = h->ro_L;
-    ra.actions = ro->actions; ra.aidx = ro->action_idx; ra.atable = ro->action_table;
-    ra.pos_tr = ro->pos_tr; ra.vel_tr = ro->vel_tr; ra.r_tr = ro->reward_tr; ra.tr_tr = ro->true_reward_tr;
-    ra.z_tr = ro->z_tr; ra.Ni_tr = ro->Ni_tr; ra.ncoll_tr = ro->ncoll_tr; ra.fin_tr = ro->finished_tr;
+    ra.TC = h->ro_TC; ra.n_actions = ro->n_actions; ra.L = h->ro_L;
+    ra.atable = ro->action_table;
     ra.agg = ro->agg; ra.done = ro->done;
     if (ro->T == 0) return DS_OK;
     DeviceGuard guard(h->device);
-    return launch_rollout(h, ra, (cudaStream_t)cuda_stream);
+    // the kernel indexes trajectory elements with 32 bits: split calls whose T * E * n does not fit
+    const size_t EN = (size_t)h->E * h->n, E = (size_t)h->E, rb = (size_t)h->real_bytes;
+    const size_t zc = (size_t)(h->k + 1) * (h->simplify ? 2 : 5);
+    const int max_T = (int)std::max<size_t>(1, (((size_t)1 << 32) - 1) / EN - (size_t)h->ro_TC);
+    auto off = [](const void *p, size_t bytes) -> void * { return p ? (char *)p + bytes : nullptr; };
+    for (int t0 = 0; t0 < ro->T; t0 += max_T) {
+        const size_t ts = (size_t)t0;
+        ra.T = (ro->T - t0 < max_T) ? ro->T - t0 : max_T;
+        ra.actions = off(ro->actions, ts * EN * 2 * rb);
+        ra.aidx = (const uint8_t *)off(ro->action_idx, ts * EN);
+        ra.pos_tr = off(ro->pos_tr, ts * EN * 2 * rb); ra.vel_tr = off(ro->vel_tr, ts * EN * 2 * rb);
+        ra.r_tr = off(ro->reward_tr, ts * EN * rb); ra.tr_tr = off(ro->true_reward_tr, ts * EN * rb);
+        ra.z_tr = off(ro->z_tr, ts * EN * zc * rb);
+        ra.Ni_tr = (int *)off(ro->Ni_tr, ts * EN * (h->k + 1) * sizeof(int32_t));
+        ra.ncoll_tr = (int *)off(ro->ncoll_tr, ts * E * sizeof(int32_t));
+        ra.fin_tr = (uint8_t *)off(ro->finished_tr, ts * E);
+        if (int rc = launch_rollout(h, ra, (cudaStream_t)cuda_stream)) return rc;
+    }
+    return DS_OK;
 }
 
 int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, void *cuda_stream)

@@ -463,8 +463,10 @@ DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
                     const typename vec2_of<Real>::type *__restrict__ s_pos,
                     const Real *__restrict__ s_delta,
                     const Real *__restrict__ s_radius,
-                    const ParamsR<Real> &P, const LogTabEntry *__restrict__ tab)
+                    const ParamsR<Real> &P, const LogTabEntry *__restrict__ tab, int cs = 1)
 {
+    // s_delta / s_radius: per-agent constants with element stride cs (1: plain arrays; 2: the
+    // rollout kernel's packed (radius, delta) pairs)
     using V2 = typename vec2_of<Real>::type;
     const int kk = (K >= 0) ? K : P.k;
     RowAcc<Real> acc;
@@ -489,9 +491,9 @@ DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
             near &= near - 1;
             const int j = j0 + jj;
             const V2 pj = s_pos[j];
-            const Real dl = s_delta[j];
+            const Real dl = s_delta[j * cs];
             PairOut<Real> po;
-            eval_pair<Real>(po, xi, yi, pj.x, pj.y, c.ds, c.radius, s_radius[j], dl, c.log_ds, P, tab);
+            eval_pair<Real>(po, xi, yi, pj.x, pj.y, c.ds, c.radius, s_radius[j * cs], dl, c.log_ds, P, tab);
             const int adj = (po.in_disk ? 1 : 0) - ((c.ds <= dl) ? 1 : 0);
             if (row_fold<Real, K>(o, acc, kk, c, j, po.d, po.logd, po.in_disk, po.coll, adj))
                 unclipped |= 1u << jj;
@@ -507,8 +509,29 @@ DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
     row_end<Real, K>(o, acc, xi, yi, c, P);
 }
 
+// Branch-free insertion of a REAL candidate (d < d_safety[i]) into the sorted list: slot m takes
+// the old slot m-1 when the candidate sorts before it, the candidate when it sorts before the old
+// slot m only.  Slots beyond k hold further sorted candidates and are never read.
+template <typename Real, int K>
+DS_HD void topk_insert(RowResult<Real, K> &o, Real d, int j)
+{
+    constexpr int CAP = RowResult<Real, K>::CAP;
+    bool lt[CAP];
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) lt[m] = d < o.td[m] || (d == o.td[m] && j < o.tj[m]);
+#pragma unroll
+    for (int m = CAP - 1; m > 0; --m) {
+        o.td[m] = lt[m - 1] ? o.td[m - 1] : (lt[m] ? d : o.td[m]);
+        o.tj[m] = lt[m - 1] ? o.tj[m - 1] : (lt[m] ? j : o.tj[m]);
+    }
+    o.td[0] = lt[0] ? d : o.td[0];
+    o.tj[0] = lt[0] ? j : o.tj[0];
+}
+
 // The same row from its segment of the evaluated work list (rollout kernel): ent[q] / res[q],
-// q < cnt, ascending j.
+// q < cnt, ascending j.  Real candidates (d < d_safety[i], self included) are sorted by
+// (d, j); the clipped agents all sit at exactly d_safety[i] behind them, so the free slots are
+// filled with the lowest clipped indices directly.
 template <typename Real, int K>
 DS_HD void eval_row_from_list(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
                               const AgentConst<Real> &c, const unsigned *__restrict__ ent,
@@ -516,32 +539,57 @@ DS_HD void eval_row_from_list(RowResult<Real, K> &o, int n, int i, Real xi, Real
                               const ParamsR<Real> &P)
 {
     using V2 = typename vec2_of<Real>::type;
+    constexpr int CAP = RowResult<Real, K>::CAP;
     const int kk = (K >= 0) ? K : P.k;
-    RowAcc<Real> acc;
-    row_begin<Real, K>(o, acc, kk, i, c);
-    unsigned unclipped_lo = (acc.self_unclipped && i < 32) ? (1u << i) : 0u;   // agents j < 32 only
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) { o.td[m] = real_inf<Real>(); o.tj[m] = 0; }
+    Real sum_local = 0, sum_all = 0;
+    int ncoll = 0, nreal = 0;
+    // j == i (:323-325): dist = 0, d_ii = min(-2 l_i, d_safety[i]), d_norm = 1 -> no barrier term
+    const Real raw_ii = sub_rn(sub_rn((Real)0, c.radius), c.radius);
+    const Real d_ii = (c.ds < raw_ii) ? c.ds : raw_ii;
+    int cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);               // :328 deltas[j], j == i
+    const bool self_unclipped = (d_ii != c.ds);
+    if (d_ii < c.ds) { o.td[0] = d_ii; o.tj[0] = i; nreal = 1; }
+    unsigned unclipped_lo = (self_unclipped && i < 32) ? (1u << i) : 0u;   // agents j < 32 only
     for (int q = 0; q < cnt; ++q) {
         const unsigned w = ent[q];
         const V2 dv = res[q];
         const int j = (int)(w & 1023u);
-        if (row_fold<Real, K>(o, acc, kk, c, j, dv.x, dv.y, (w >> 10) & 1u, (w >> 11) & 1u,
-                              (int)((w >> 12) & 3u) - 1))
+        cnt_nd += (int)((w >> 12) & 3u) - 1;                            // replaces the clipped-pair count
+        if (dv.x != c.ds) {                                             // not clipped (NaN included)
             if (j < 32) unclipped_lo |= 1u << j;
-    }
-    // clipped agents tie at exactly d_safety[i]: offered in index order until one is refused
-    // (a refusal is final: later real candidates can only push entries out)
-    for (int cj = 0; cj < n; ++cj) {
-        bool unclipped;
-        if (cj < 32) {
-            unclipped = (unclipped_lo >> cj) & 1u;
-        } else {
-            unclipped = (cj == i) && acc.self_unclipped;
-            for (int q = 0; q < cnt; ++q)
-                if ((int)(ent[q] & 1023u) == cj && res[q].x != c.ds) unclipped = true;
+            ncoll += (int)((w >> 11) & 1u);
+            sum_all = add_rn(sum_all, dv.y);                                                    // :283
+            sum_local = add_rn(sum_local, mul_rn(dv.y, ((w >> 10) & 1u) ? (Real)1 : (Real)0));  // :282
+            if (dv.x < c.ds) { topk_insert<Real, K>(o, dv.x, j); ++nreal; }
         }
-        if (unclipped) continue;
-        if (!topk_offer<Real, K>(o, kk, c.ds, cj)) break;
     }
+    // free slots <- lowest clipped indices (d = d_safety[i] for all of them: index order)
+    unsigned cm = ~unclipped_lo;
+    if (n < 32) cm &= (1u << n) - 1u;
+    int hi = 32;                                                        // next index to test when n > 32
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) {
+        if (m <= kk && m >= nreal) {
+            int cj = n;
+            if (cm) {
+                cj = lowest_bit(cm);
+                cm &= cm - 1;
+            } else {
+                for (; hi < n && cj == n; ++hi) {                       // rare: >= 32 - k agents unclipped
+                    bool unclipped = (hi == i) && self_unclipped;
+                    for (int q = 0; q < cnt; ++q)
+                        if ((int)(ent[q] & 1023u) == hi && res[q].x != c.ds) unclipped = true;
+                    if (!unclipped) cj = hi;
+                }
+            }
+            if (cj < n) { o.td[m] = c.ds; o.tj[m] = cj; }
+        }
+    }
+    RowAcc<Real> acc;
+    acc.sum_local = sum_local; acc.sum_all = sum_all; acc.ncoll = ncoll; acc.cnt_nd = cnt_nd;
+    acc.self_unclipped = self_unclipped;
     row_end<Real, K>(o, acc, xi, yi, c, P);
 }
 
@@ -553,7 +601,7 @@ DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
                      const typename vec2_of<Real>::type *__restrict__ s_vel,
                      const Real *__restrict__ s_radius,
                      const ParamsR<Real> &P, Real *__restrict__ z, int *__restrict__ Ni,
-                     size_t g)
+                     size_t g, int cs = 1)
 {
     using V2 = typename vec2_of<Real>::type;
     const int kk = (K >= 0) ? K : P.k;
@@ -611,7 +659,7 @@ DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
                 }
                 const V2 vj = s_vel[j];                               // zj = state[j,:].copy() (:367,385)
                 Real *row = zr + kth * 5;
-                row[0] = a; row[1] = bq; row[2] = vj.x; row[3] = vj.y; row[4] = s_radius[j];
+                row[0] = a; row[1] = bq; row[2] = vj.x; row[3] = vj.y; row[4] = s_radius[j * cs];
             }
         }
     }
@@ -718,64 +766,75 @@ step_kernel(const StepArgs a)
 
 // ---------------------------------------------------------------- rollout kernel
 // Shared memory of a rollout CTA.  Per CTA: constants [n], log table, work list [L].  Per row
-// (I = TC*G*n): action, position, r, true_r.  Per agent of a slice (A = G*n): chunk start
-// position, last executed velocity.  Per frame (F = TC*G): collision count, not-at-goal flag,
-// frame info, per-frame means.  Per environment (G): alive, t, executed slices.
+// (I = TC*G*n), double buffered over chunks: action, position; single: r, true_r.  Per agent of
+// a slice (A = G*n): chunk start position, last executed velocity.  Per frame (F = TC*G):
+// collision count, not-at-goal flag, frame info, per-frame means.  Per environment (G): alive,
+// t, executed slices of the chunk.
 template <typename Real> struct RoSmem {
     using V2 = typename vec2_of<Real>::type;
-    Real *delta, *radius, *dsafe, *logds;
+    V2 *cA;                  // [n] (d_safety, log d_safety)
+    V2 *cB;                  // [n] (radius, delta)
+    V2 *cF;                  // [n] end point
     LogTabEntry *logtab;
-    V2 *act, *pos, *p0, *vfin, *res;
+    V2 *act_, *pos_, *p0, *vfin, *res;   // act_ / pos_: two buffers of I rows (chunk parity)
+    int I_, G_;
     Real *r, *tr;
     unsigned *ent;
     double *mr, *mtr;
-    int *cnt, *notgoal, *finfo, *alive, *tenv, *nexec, *lcount;
+    int *cnt, *notgoal, *finfo, *alive_, *tenv_, *nexec, *lcount;   // alive_ / tenv_: per chunk parity
+    __device__ V2 *act(int b) const { return act_ + b * I_; }
+    __device__ V2 *pos(int b) const { return pos_ + b * I_; }
+    __device__ int *alive(int b) const { return alive_ + b * G_; }
+    __device__ int *tenv(int b) const { return tenv_ + b * G_; }
     __host__ __device__ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
     __host__ __device__ static size_t bytes(int n, int G, int TC, int L)
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
-        return align16(4 * n * sizeof(Real)) + kLogTabSize * sizeof(LogTabEntry) +
-               (2 * I + 2 * A + (size_t)L) * sizeof(V2) + align16(2 * I * sizeof(Real)) +
-               align16((size_t)L * sizeof(unsigned)) + 2 * F * sizeof(double) +
-               align16(3 * F * sizeof(int)) + align16((3 * (size_t)G + 1) * sizeof(int));
+        return (3 * (size_t)n + 4 * I + 2 * A + (size_t)L) * sizeof(V2) + kLogTabSize * sizeof(LogTabEntry) +
+               align16(2 * I * sizeof(Real)) + align16((size_t)L * sizeof(unsigned)) + 2 * F * sizeof(double) +
+               align16(3 * F * sizeof(int)) + align16((5 * (size_t)G + 1) * sizeof(int));
     }
     __device__ RoSmem(unsigned char *base, int n, int G, int TC, int L)
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
         unsigned char *p = base;
-        delta = reinterpret_cast<Real *>(p); radius = delta + n; dsafe = radius + n; logds = dsafe + n;
-        p += align16(4 * n * sizeof(Real));
+        cA = reinterpret_cast<V2 *>(p); cB = cA + n; cF = cB + n;
+        I_ = (int)I; G_ = G;
+        act_ = cF + n; pos_ = act_ + 2 * I;
+        p0 = pos_ + 2 * I; vfin = p0 + A; res = vfin + A;
+        p += (3 * (size_t)n + 4 * I + 2 * A + (size_t)L) * sizeof(V2);
         logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);
-        act = reinterpret_cast<V2 *>(p); pos = act + I; p0 = pos + I; vfin = p0 + A; res = vfin + A;
-        p += (2 * I + 2 * A + (size_t)L) * sizeof(V2);
         r = reinterpret_cast<Real *>(p); tr = r + I; p += align16(2 * I * sizeof(Real));
         ent = reinterpret_cast<unsigned *>(p); p += align16((size_t)L * sizeof(unsigned));
         mr = reinterpret_cast<double *>(p); mtr = mr + F; p += 2 * F * sizeof(double);
         cnt = reinterpret_cast<int *>(p); notgoal = cnt + F; finfo = notgoal + F; p += align16(3 * F * sizeof(int));
-        alive = reinterpret_cast<int *>(p); tenv = alive + G; nexec = tenv + G; lcount = nexec + G;
+        alive_ = reinterpret_cast<int *>(p); tenv_ = alive_ + 2 * G; nexec = tenv_ + 2 * G; lcount = nexec + G;
     }
 };
 
-// frame info word written by the frame's leader thread after the rows are evaluated
 #ifndef DS_RO_MINB
 #define DS_RO_MINB 2      // CTAs of 256 threads per SM the rollout kernel is compiled for (register cap)
 #endif
+// frame info word written by the frame's leader thread after the rows are evaluated
 constexpr int kFrameExec = 1, kFrameFin = 2, kFrameLast = 4;
 
 // T fused steps, TC time slices per chunk evaluated concurrently (see the header comment).
 // NB = number of 32-agent blocks whose near masks a row keeps in registers (n <= 32 NB);
-// NB == 0: any n, masks in local memory.
+// NB == 0: any n, masks in local memory.  Element indices are 32 bit: the host splits a call
+// whose T * E * n would not fit.
 //
-// One chunk:
-//   (a) actions of the chunk -> smem                                             | barrier
-//   (b) threads < A integrate their agent through the chunk's slices -> pos[]    | barrier
-//   (c) every row: pass 1 over its frame -> near masks; a warp scan + one smem atomic per
-//       warp gives the row a contiguous segment of the work list; entries written | barrier
-//   (d) all threads: one near pair per thread per round (eval_pair)              | barrier
+// Staging of chunk c (buffer c & 1), overlapped with the tail of chunk c - 1: the rows put their
+// prefetched actions into act[], then one thread per agent integrates through the chunk's slices
+// (sequential, bit-exact: A = I, B = dt I, drone_env.py:78-79,235) into pos[].
+// One chunk, five barriers:
+//   (c) every row: pass 1 over its frame -> near masks; a warp scan + one smem atomic per warp
+//       gives the row a contiguous segment of the work list; entries written          | barrier
+//   (d) all threads: one near pair per thread per round (eval_pair)                   | barrier
 //   (e) every row folds its segment, finishes the row, posts r / true_r / collision count /
-//       not-at-goal to its frame                                                 | barrier
-//   (f) threads < F: leader of one frame each -- executed?, finished?, frame means   | barrier
-//   (g) every executed row stores its outputs; threads < G accumulate the episode sums.
+//       not-at-goal to its frame; actions of the next chunk -> act[]                  | barrier
+//   (f) threads < F: leader of one frame each -- executed?, finished?, frame means    | barrier
+//   (g) every executed row stores its outputs; threads < G accumulate the episode sums and
+//       advance t / alive; threads < A integrate the next chunk                       | barrier
 template <typename Real, int K, int NT, int NB>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? DS_RO_MINB : 1)
 rollout_kernel(const RolloutArgs ra)
@@ -786,38 +845,38 @@ rollout_kernel(const RolloutArgs ra)
     const int n = a.n, G = a.G, TC = ra.TC, E = a.E, T = ra.T, L = ra.L;
     RoSmem<Real> sm(smem_raw, n, G, TC, L);
     for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-        sm.delta[idx] = ((const Real *)a.c.delta)[idx];
-        sm.radius[idx] = ((const Real *)a.c.radius)[idx];
-        sm.dsafe[idx] = ((const Real *)a.c.d_safety)[idx];
-        sm.logds[idx] = ((const Real *)a.c.log_ds)[idx];
+        V2 v;
+        v.x = ((const Real *)a.c.d_safety)[idx]; v.y = ((const Real *)a.c.log_ds)[idx]; sm.cA[idx] = v;
+        v.x = ((const Real *)a.c.radius)[idx]; v.y = ((const Real *)a.c.delta)[idx]; sm.cB[idx] = v;
+        sm.cF[idx] = reinterpret_cast<const V2 *>(a.c.xF)[idx];
     }
     if (sizeof(Real) == 8)
         for (int idx = threadIdx.x; idx < kLogTabSize; idx += blockDim.x) sm.logtab[idx] = a.c.logtab[idx];
     const ParamsR<Real> P(a);
     const int kk = (K >= 0) ? K : a.k;
-    const int cols = a.simplify ? 2 : 5;
     const int A = G * n;                              // agents per slice in this CTA
     const int F = G * TC;                             // frames per chunk in this CTA
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int s = tid / A, ag = tid - s * A;          // time slice within the chunk, agent slot
     const int le = ag / n, i = ag - le * n;
-    const long long e = (long long)blockIdx.x * G + le;
+    const int e = blockIdx.x * G + le;
     const bool active = (s < TC) && (e < E);
-    const size_t g = active ? (size_t)e * n + i : 0;
-    const size_t EN = (size_t)E * n;
+    const unsigned g = active ? (unsigned)e * n + i : 0u;
+    const unsigned EN = (unsigned)E * n;
     const int fr = s * G + le;                        // frame slot of this thread
     const V2 *atab = reinterpret_cast<const V2 *>(ra.atable);
+    const Real thr2 = active ? ((const Real *)a.c.thr2)[i] : (Real)0;
+    const int clipcnt = active ? a.c.clipcnt[i] : 0;
+    const bool agent_thread = tid < A && e < E;       // s == 0: owns agent ag across the call
 
-    AgentConst<Real> c{};
-    if (active) c = load_agent_const<Real>(a.c, i);
-    if (active && s == 0) {
-        sm.p0[ag] = reinterpret_cast<const V2 *>(a.pos)[g];
-        sm.vfin[ag] = reinterpret_cast<const V2 *>(a.vel)[g];
-        if (i == 0) { sm.alive[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv[le] = a.t[e]; sm.nexec[le] = 0; }
+    if (agent_thread) {
+        sm.p0[tid] = reinterpret_cast<const V2 *>(a.pos)[g];
+        sm.vfin[tid] = reinterpret_cast<const V2 *>(a.vel)[g];
+        if (i == 0) { sm.alive(0)[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv(0)[le] = a.t[e]; }
     }
     // per-environment episode accumulators live in thread le (< G)
-    const long long e_acc = (long long)blockIdx.x * G + tid;
+    const int e_acc = blockIdx.x * G + tid;
     const bool acc_thread = tid < G && e_acc < E;
     double acc_r = 0, acc_tr = 0, acc_c = 0, acc_s = 0;
     if (acc_thread) {
@@ -826,43 +885,46 @@ rollout_kernel(const RolloutArgs ra)
     }
     bool stepped = false;
 
-    auto load_action = [&](int t) -> V2 {
-        const size_t at = (size_t)t * EN + g;
+    auto load_action = [&](unsigned at) -> V2 {
         if (ra.actions) return reinterpret_cast<const V2 *>(ra.actions)[at];
         return atab[ra.aidx[at]];
     };
-    V2 u_next{};
-    if (active && s < T) u_next = load_action(s);
+    // sequential integration of one agent through the nsl slices of a chunk
+    auto integrate = [&](int buf, int nsl) {
+        V2 p = sm.p0[tid];
+        const V2 *ua = sm.act(buf) + tid;
+        V2 *pa = sm.pos(buf) + tid;
+        for (int q = 0; q < nsl; ++q) {
+            const V2 uq = ua[q * A];
+            p.x = add_rn(p.x, mul_rn(P.dt, uq.x));
+            p.y = add_rn(p.y, mul_rn(P.dt, uq.y));
+            pa[q * A] = p;
+        }
+    };
+    unsigned at = (unsigned)s * EN + g;               // element index of this row at slice t0 + s
+    unsigned fe = (unsigned)s * E + (unsigned)e;
+    V2 u{}, u_next{};
+    if (active && s < T) u = load_action(at);
+    if (active && TC + s < T) u_next = load_action(at + (unsigned)TC * EN);
+    // stage chunk 0
+    if (active && s < T) sm.act(0)[tid] = u;
+    if (tid == 0) *sm.lcount = 0;
+    __syncthreads();
+    if (agent_thread && sm.alive(0)[le] != 0) integrate(0, (T < TC) ? T : TC);
+    __syncthreads();
 
-    for (int t0 = 0; t0 < T; t0 += TC) {
+    for (int t0 = 0, buf = 0; t0 < T; t0 += TC, buf ^= 1) {
         const int nsl = (T - t0 < TC) ? (T - t0) : TC;      // slices in this chunk
         const bool in_chunk = active && s < nsl;
-        const V2 u = u_next;
-        if (active && t0 + TC + s < T) u_next = load_action(t0 + TC + s);   // prefetch the next chunk
-        // (a)
-        if (in_chunk) sm.act[tid] = u;
-        if (tid == 0) *sm.lcount = 0;
-        __syncthreads();
-        // (b) sequential single-integrator steps, one thread per agent (A = I, B = dt I, :78-79,235)
-        if (tid < A && e < E && sm.alive[le] != 0) {
-            V2 p = sm.p0[tid];
-            for (int q = 0; q < nsl; ++q) {
-                const V2 uq = sm.act[q * A + tid];
-                p.x = add_rn(p.x, mul_rn(P.dt, uq.x));
-                p.y = add_rn(p.y, mul_rn(P.dt, uq.y));
-                sm.pos[q * A + tid] = p;
-            }
-        }
-        __syncthreads();
         // (c) pass 1
-        const bool valid = in_chunk && sm.alive[le] != 0;
+        const bool valid = in_chunk && sm.alive(buf)[le] != 0;
         V2 p{};
         constexpr int NBR = (NB > 0) ? NB : 32;
         unsigned near[NBR];
         int ncnt = 0;
-        const V2 *fpos = sm.pos + s * A + le * n;            // positions of this row's frame
+        const V2 *fpos = sm.pos(buf) + (tid - i);           // positions of this row's frame
         if (valid) {
-            p = sm.pos[tid];
+            p = fpos[i];
             if (i == 0) { sm.cnt[fr] = 0; sm.notgoal[fr] = 0; }
             if (NB > 0) {
 #pragma unroll
@@ -876,7 +938,7 @@ rollout_kernel(const RolloutArgs ra)
                             const V2 pj = fpos[j0 + jj];
                             const Real dx = sub_rn(p.x, pj.x), dy = sub_rn(p.y, pj.y);
                             const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
-                            m |= ((d2 >= c.thr2) ? 0u : 1u) << jj;          // NaN -> near (exact path)
+                            m |= ((d2 >= thr2) ? 0u : 1u) << jj;            // NaN -> near (exact path)
                         }
                         if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
                     }
@@ -892,7 +954,7 @@ rollout_kernel(const RolloutArgs ra)
                         const V2 pj = fpos[j0 + jj];
                         const Real dx = sub_rn(p.x, pj.x), dy = sub_rn(p.y, pj.y);
                         const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
-                        m |= ((d2 >= c.thr2) ? 0u : 1u) << jj;
+                        m |= ((d2 >= thr2) ? 0u : 1u) << jj;
                     }
                     if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
                     near[bk] = m;
@@ -913,8 +975,9 @@ rollout_kernel(const RolloutArgs ra)
         const int seg = wbase + incl - ncnt;
         const bool listed = ncnt == 0 || seg + ncnt <= L;    // otherwise the row evaluates itself in (e)
         if (valid && ncnt > 0) {
-            int q = seg;
+            unsigned *ep = sm.ent + seg;
             if (listed) {
+                const unsigned base = (unsigned)tid | ((unsigned)i << 20);
                 const int nb = (NB > 0) ? NBR : (n + 31) / 32;
 #pragma unroll
                 for (int bk = 0; bk < nb; ++bk) {
@@ -922,11 +985,11 @@ rollout_kernel(const RolloutArgs ra)
                     while (m) {
                         const int jj = lowest_bit(m);
                         m &= m - 1;
-                        sm.ent[q++] = pack_entry(tid, bk * 32 + jj, i);
+                        *ep++ = base | ((unsigned)(bk * 32 + jj) << 10);
                     }
                 }
             } else {
-                for (; q < L && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
+                for (int q = seg; q < L && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
             }
         }
         __syncthreads();
@@ -937,38 +1000,43 @@ rollout_kernel(const RolloutArgs ra)
                 const unsigned w = sm.ent[q];
                 if (w == kEntSkip) continue;
                 const int row = (int)(w & 1023u), j = (int)((w >> 10) & 1023u), ri = (int)(w >> 20);
-                const V2 pi = sm.pos[row], pj = sm.pos[row - ri + j];
-                const Real ds_i = sm.dsafe[ri], dl = sm.delta[j];
+                const V2 pi = sm.pos(buf)[row], pj = sm.pos(buf)[row - ri + j];
+                const V2 ca = sm.cA[ri], cbi = sm.cB[ri], cbj = sm.cB[j];
                 PairOut<Real> po;
-                eval_pair<Real>(po, pi.x, pi.y, pj.x, pj.y, ds_i, sm.radius[ri], sm.radius[j], dl, sm.logds[ri], P,
-                                sm.logtab);
+                eval_pair<Real>(po, pi.x, pi.y, pj.x, pj.y, ca.x, cbi.x, cbj.x, cbj.y, ca.y, P, sm.logtab);
                 V2 dv; dv.x = po.d; dv.y = po.logd;
                 sm.res[q] = dv;
-                sm.ent[q] = pack_result(j, po.in_disk, po.coll, (po.in_disk ? 1 : 0) - ((ds_i <= dl) ? 1 : 0) + 1);
+                sm.ent[q] = pack_result(j, po.in_disk, po.coll, (po.in_disk ? 1 : 0) - ((ca.x <= cbj.y) ? 1 : 0) + 1);
             }
         }
         __syncthreads();
         // (e) rows
         RowResult<Real, K> o;
+        AgentConst<Real> c;
         if (valid) {
+            const V2 ca = sm.cA[i], cb = sm.cB[i], cf = sm.cF[i];
+            c.xF = cf.x; c.yF = cf.y; c.ds = ca.x; c.log_ds = ca.y; c.radius = cb.x; c.delta = cb.y;
+            c.thr2 = thr2; c.clipcnt = clipcnt;
             if (listed)
                 eval_row_from_list<Real, K>(o, n, i, p.x, p.y, c, sm.ent + seg, sm.res + seg, ncnt, P);
             else
-                eval_row<Real, K>(o, n, i, p.x, p.y, c, fpos, sm.delta, sm.radius, P, sm.logtab);
+                eval_row<Real, K>(o, n, i, p.x, p.y, c, fpos, &sm.cB[0].y, &sm.cB[0].x, P, sm.logtab, 2);
             sm.r[tid] = o.r;
             sm.tr[tid] = o.tr;
             if (o.ncoll) atomicAdd(&sm.cnt[fr], o.ncoll);
             if (!o.at_goal) sm.notgoal[fr] = 1;
         }
+        if (tid == 0) *sm.lcount = 0;                        // every thread has read it in (d)
+        // actions of the next chunk (read by the integration in (g), after two more barriers)
+        if (active && t0 + TC + s < T) sm.act(buf ^ 1)[tid] = u_next;
         __syncthreads();
         // (f) frame leaders: a slice executes iff no earlier slice of this chunk finished the
         // episode (:248-256); frame means for the episode sums (train_problem.py:98-100)
         if (tid < F) {
             const int fs = tid / G, fle = tid - fs * G;      // slice, local environment of frame tid
-            const long long fe_ = (long long)blockIdx.x * G + fle;
             int info = 0;
-            if (fe_ < E && fs < nsl && sm.alive[fle] != 0) {
-                const int ft0 = sm.tenv[fle];
+            if (blockIdx.x * G + fle < E && fs < nsl && sm.alive(buf)[fle] != 0) {
+                const int ft0 = sm.tenv(buf)[fle];
                 bool exec = true;
                 for (int q = 0; q < fs; ++q)
                     if (sm.notgoal[q * G + fle] == 0 || ft0 + q >= a.max_steps - 1) exec = false;
@@ -980,35 +1048,32 @@ rollout_kernel(const RolloutArgs ra)
                     const Real *rr = sm.r + fs * A + fle * n, *rt = sm.tr + fs * A + fle * n;
                     for (int j = 0; j < n; ++j) { sr += (double)rr[j]; st += (double)rt[j]; }
                     sm.mr[tid] = sr / n; sm.mtr[tid] = st / n;
+                    if (last) sm.nexec[fle] = fs + 1 + (fin ? 0x10000 : 0);
                 }
             }
             sm.finfo[tid] = info;
         }
         __syncthreads();
         // (g) stores
-        const size_t at = (size_t)(t0 + s) * EN + g;
-        const size_t fe = (size_t)(t0 + s) * E + (size_t)e;
         if (valid) {
             const int info = sm.finfo[fr];
             if (info & kFrameExec) {
                 const int nc = sm.cnt[fr];
-                const bool fin = (info & kFrameFin) != 0, last = (info & kFrameLast) != 0;
-                const V2 *fvel = sm.act + s * A + le * n;
+                const bool fin = (info & kFrameFin) != 0;
+                const V2 *fvel = sm.act(buf) + (tid - i);
                 if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
                 if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = u;              // :238
                 if (ra.r_tr) reinterpret_cast<Real *>(ra.r_tr)[at] = o.r;
                 if (ra.tr_tr) reinterpret_cast<Real *>(ra.tr_tr)[at] = o.tr;
                 if (ra.z_tr)
-                    write_obs<Real, K>(o, i, p.x, p.y, c, fpos, fvel, sm.radius, P,
-                                       reinterpret_cast<Real *>(ra.z_tr) + (size_t)(t0 + s) * EN * (kk + 1) * cols,
-                                       ra.Ni_tr + (size_t)(t0 + s) * EN * (kk + 1), g);
-                if (last) { sm.p0[ag] = p; sm.vfin[ag] = u; }
+                    write_obs<Real, K>(o, i, p.x, p.y, c, fpos, fvel, &sm.cB[0].x, P,
+                                       reinterpret_cast<Real *>(ra.z_tr), ra.Ni_tr, at, 2);
                 if (fin || t0 + s == T - 1) {
                     // last executed step of the call: leave the step()-style outputs in the live buffers
                     reinterpret_cast<Real *>(a.r)[g] = o.r;
                     reinterpret_cast<Real *>(a.tr)[g] = o.tr;
-                    write_obs<Real, K>(o, i, p.x, p.y, c, fpos, fvel, sm.radius, P,
-                                       reinterpret_cast<Real *>(a.z), a.Ni, g);
+                    write_obs<Real, K>(o, i, p.x, p.y, c, fpos, fvel, &sm.cB[0].x, P,
+                                       reinterpret_cast<Real *>(a.z), a.Ni, g, 2);
                     if (i == 0) { a.ncoll[e] = nc; a.fin[e] = fin ? 1 : 0; }
                 }
                 if (i == 0) {
@@ -1021,37 +1086,45 @@ rollout_kernel(const RolloutArgs ra)
         } else if (in_chunk && i == 0 && ra.fin_tr) {
             ra.fin_tr[fe] = 2;
         }
-        // episode sums of this chunk, in time order; environment bookkeeping for the next chunk
-        // (alive / tenv are read again only after the next chunk's first barrier)
-        if (acc_thread && sm.alive[tid] != 0) {
+        // one thread per agent: state after the chunk's last executed slice; next chunk's positions
+        if (agent_thread && sm.alive(buf)[le] != 0) {
+            const int ne = sm.nexec[le] & 0xffff;
+            sm.p0[tid] = sm.pos(buf)[(ne - 1) * A + tid];
+            sm.vfin[tid] = sm.act(buf)[(ne - 1) * A + tid];
+            if (!(sm.nexec[le] & 0x10000) && t0 + TC < T)
+                integrate(buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
+        }
+        // episode sums of this chunk, in time order; t / alive of the next chunk (other parity)
+        if (acc_thread) {
             int ne = 0;
-            for (int q = 0; q < nsl; ++q) {
-                const int info = sm.finfo[q * G + tid];
-                if (!(info & kFrameExec)) break;
-                acc_r += sm.mr[q * G + tid]; acc_tr += sm.mtr[q * G + tid];
-                acc_c += (double)sm.cnt[q * G + tid]; acc_s += 1;
-                ++ne;
+            bool env_fin = false;
+            const bool was_alive = sm.alive(buf)[tid] != 0;
+            if (was_alive) {
+                ne = sm.nexec[tid] & 0xffff;
+                env_fin = (sm.nexec[tid] & 0x10000) != 0;
+                for (int q = 0; q < ne; ++q) {
+                    acc_r += sm.mr[q * G + tid]; acc_tr += sm.mtr[q * G + tid];
+                    acc_c += (double)sm.cnt[q * G + tid]; acc_s += 1;
+                }
+                stepped = true;
             }
-            if (ne) stepped = true;
-            sm.nexec[tid] = ne;
+            sm.tenv(buf ^ 1)[tid] = sm.tenv(buf)[tid] + ne;
+            sm.alive(buf ^ 1)[tid] = (was_alive && !env_fin) ? 1 : 0;
         }
+        u = u_next;
+        at += (unsigned)TC * EN; fe += (unsigned)TC * E;
+        if (active && t0 + 2 * TC + s < T) u_next = load_action(at + (unsigned)TC * EN);   // prefetch
         __syncthreads();
-        if (acc_thread && sm.alive[tid] != 0) {
-            // after the barrier: every row of this chunk has read alive / tenv
-            const int ne = sm.nexec[tid];
-            sm.tenv[tid] += ne;
-            if (ne > 0 && (sm.finfo[(ne - 1) * G + tid] & kFrameFin)) sm.alive[tid] = 0;
-        }
     }
-    __syncthreads();
-    if (active && s == 0) {
-        reinterpret_cast<V2 *>(a.pos)[g] = sm.p0[ag];
-        reinterpret_cast<V2 *>(a.vel)[g] = sm.vfin[ag];
+    const int fbuf = ((T + TC - 1) / TC) & 1;                // parity the last chunk wrote
+    if (agent_thread) {
+        reinterpret_cast<V2 *>(a.pos)[g] = sm.p0[tid];
+        reinterpret_cast<V2 *>(a.vel)[g] = sm.vfin[tid];
     }
     if (acc_thread) {
-        a.t[e_acc] = sm.tenv[tid];
+        a.t[e_acc] = sm.tenv(fbuf)[tid];
         if (stepped) {
-            if (sm.alive[tid] == 0) ra.done[e_acc] = 1;
+            if (sm.alive(fbuf)[tid] == 0) ra.done[e_acc] = 1;
             double *ag4 = ra.agg + (size_t)e_acc * 4;
             ag4[0] = acc_r; ag4[1] = acc_tr; ag4[2] = acc_c; ag4[3] = acc_s;
         }

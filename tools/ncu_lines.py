@@ -26,7 +26,7 @@ def main(rep, kern, top=45):
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)), m.group(3).strip())
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
+        if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l):
             lines.append((cur, l.strip()))
     if len(lines) != len(sass):
         print(f"warning: {len(lines)} disassembled instr vs {len(sass)} in report", file=sys.stderr)
