@@ -43,6 +43,7 @@ struct ds_handle {
     size_t step_smem;
     int ro_G, ro_TC, ro_threads, ro_blocks;
     int ro_L, ro_NB;          // work-list capacity; near-mask words kept in registers (0 = any n)
+    int ro_inline;            // n <= 32: rows evaluate their own near pairs instead of the work list
     size_t ro_smem;
     size_t smem_optin;
     // device constants (Real typed unless noted)
@@ -100,7 +101,9 @@ int upload_consts(ds_handle *h, const ds_config *cfg)
             t2 = thr * thr * (1 + m);
         }
         thr2[i] = (Real)t2;
-        if (!(thr2[i] >= t2)) thr2[i] = (Real)INFINITY;   // never round the threshold down
+        if (!(thr2[i] >= t2))                              // never round the threshold down
+            thr2[i] = (sizeof(Real) == 8) ? (Real)std::nextafter((double)thr2[i], (double)INFINITY)
+                                          : (Real)std::nextafterf((float)thr2[i], INFINITY);
         int cc = 0;
         for (int j = 0; j < n; ++j)
             if (j != i && dsv[i] <= dl[j]) ++cc;            // :328 for a clipped pair, evaluated in Real
@@ -175,6 +178,8 @@ void plan_launch(ds_handle *h)
     int per_row = (n - 1 < env_int("DS_PLAN_LPR", 6)) ? (n - 1) : env_int("DS_PLAN_LPR", 6);
     per_row = per_row < 1 ? 1 : per_row;
     h->ro_NB = n <= 32 ? 1 : (n <= 128 ? 4 : 0);
+    h->ro_inline = (n <= 32) ? env_int("DS_PLAN_INLINE", 0) : 0;
+    if (h->ro_inline) per_row = 1;                         // the list only serves the final reduction
     for (;; --per_row) {
         h->ro_L = bestG * n * bestTC * per_row;
         h->ro_smem = rollout_smem(h, bestG, bestTC, h->ro_L);
@@ -430,6 +435,7 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_
         return fail(DS_ERR_ARG, "ds_rollout: z_tr and Ni_tr must be given together");
     ra.s.G = h->ro_G;
     ra.TC = h->ro_TC; ra.n_actions = ro->n_actions; ra.L = h->ro_L;
+    ra.inline_rows = h->ro_inline;
     ra.atable = ro->action_table;
     ra.agg = ro->agg; ra.done = ro->done;
     if (ro->T == 0) return DS_OK;

@@ -279,6 +279,7 @@ struct RolloutArgs {
     StepArgs s;
     int T, TC, n_actions;
     int L;                   // capacity of the CTA's near-pair work list
+    int inline_rows;         // n <= 32 only: rows evaluate their own near pairs (no work list)
     const void *actions;     // Real [T][E][n][2] or null
     const uint8_t *aidx;     // u8 [T][E][n]
     const void *atable;      // Real [n_actions][2]
@@ -335,22 +336,25 @@ DS_HD void eval_pair(PairOut<Real> &po, Real xi, Real yi, Real xj, Real yj, Real
     const Real dist = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));     // :318 (BLAS ddot)
     const Real raw = sub_rn(sub_rn(dist, rad_i), rad_j);           // :318
     Real d = (ds_i < raw) ? ds_i : raw;                            // python min(raw, d_safety[i])
-    if (d == (Real)0) d = P.zero_eps;                              // :319-320
+    d = (d == (Real)0) ? P.zero_eps : d;                           // :319-320
     po.d = d;
     po.in_disk = d <= delta_j;                                     // :328 deltas[j]
-    po.logd = (Real)0;
-    po.coll = false;
-    if (d != ds_i) {
-        // not clipped: d_ij_norm != 1, the barrier term is live (:321,327,330-332)
-        if (P.log_mode == 0) {
-            const Real dn = div_rn(ds_i, d);
-            po.coll = dn <= (Real)0;
-            po.logd = po.coll ? P.sentinel : log_r(dn, tab);
-        } else {
-            po.coll = (ds_i > (Real)0) ? (d < (Real)0) : (ds_i == (Real)0);
-            po.logd = po.coll ? P.sentinel : sub_rn(log_ds_i, log_r(fabs(d), tab));
-        }
+    // not clipped: d_ij_norm != 1, the barrier term is live (:321,327,330-332).  Straight-line:
+    // near pairs are almost never clipped, so the log is evaluated for all of them (on 1 where its
+    // value is not used) and selected.
+    const bool live = d != ds_i;
+    bool coll;
+    Real lg;
+    if (P.log_mode == 0) {
+        const Real dn = div_rn(ds_i, d);
+        coll = dn <= (Real)0;
+        lg = log_r((live && !coll) ? dn : (Real)1, tab);
+    } else {
+        coll = (ds_i > (Real)0) ? (d < (Real)0) : (ds_i == (Real)0);
+        lg = sub_rn(log_ds_i, log_r((live && !coll) ? fabs(d) : fabs(ds_i), tab));
     }
+    po.coll = live && coll;
+    po.logd = live ? (coll ? P.sentinel : lg) : (Real)0;
 }
 
 // Near-pair work-list entry (rollout kernel).  Before evaluation: row | j << 10 | i << 20.
@@ -509,16 +513,19 @@ DS_HD void eval_row(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
     row_end<Real, K>(o, acc, xi, yi, c, P);
 }
 
-// Branch-free insertion of a REAL candidate (d < d_safety[i]) into the sorted list: slot m takes
-// the old slot m-1 when the candidate sorts before it, the candidate when it sorts before the old
-// slot m only.  Slots beyond k hold further sorted candidates and are never read.
+// k-nearest selection for the work-list / near-mask paths.  Neighbour candidates (d < d_safety[i])
+// arrive in ASCENDING j, so a strict "d < slot" insertion keeps equal distances in index order --
+// the stable argsort order (np.argsort row, :338) -- with one compare per slot.  Only the row's own
+// entry (j = i) is out of order; it is merged afterwards with the full (d, j) rule.  CAP = k + 1
+// neighbours are tracked because self may fall outside the first k + 1 (coincident agents, or a
+// larger neighbour radius).
 template <typename Real, int K>
-DS_HD void topk_insert(RowResult<Real, K> &o, Real d, int j)
+DS_HD void topk_insert_sorted(RowResult<Real, K> &o, Real d, int j)
 {
     constexpr int CAP = RowResult<Real, K>::CAP;
     bool lt[CAP];
 #pragma unroll
-    for (int m = 0; m < CAP; ++m) lt[m] = d < o.td[m] || (d == o.td[m] && j < o.tj[m]);
+    for (int m = 0; m < CAP; ++m) lt[m] = d < o.td[m];             // false for d = +inf / NaN
 #pragma unroll
     for (int m = CAP - 1; m > 0; --m) {
         o.td[m] = lt[m - 1] ? o.td[m - 1] : (lt[m] ? d : o.td[m]);
@@ -528,10 +535,50 @@ DS_HD void topk_insert(RowResult<Real, K> &o, Real d, int j)
     o.tj[0] = lt[0] ? j : o.tj[0];
 }
 
+// Merge the row's own entry (d_ii, i) into the sorted neighbours.
+template <typename Real, int K>
+DS_HD void topk_merge_self(RowResult<Real, K> &o, Real d_ii, int i)
+{
+    constexpr int CAP = RowResult<Real, K>::CAP;
+    bool lt[CAP];
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) lt[m] = d_ii < o.td[m] || (d_ii == o.td[m] && i < o.tj[m]);
+#pragma unroll
+    for (int m = CAP - 1; m > 0; --m) {
+        o.td[m] = lt[m - 1] ? o.td[m - 1] : (lt[m] ? d_ii : o.td[m]);
+        o.tj[m] = lt[m - 1] ? o.tj[m - 1] : (lt[m] ? i : o.tj[m]);
+    }
+    o.td[0] = lt[0] ? d_ii : o.td[0];
+    o.tj[0] = lt[0] ? i : o.tj[0];
+}
+
+// Free slots <- lowest clipped indices (all at exactly d_safety[i]: index order).  nreal = real
+// candidates found (self included); cm = clipped agents j < 32; scan(hi) tells whether agent
+// hi >= 32 is unclipped (rare path: >= 32 - k of the first 32 agents unclipped).
+template <typename Real, int K, typename ScanF>
+DS_HD void topk_fill_clipped(RowResult<Real, K> &o, int kk, int n, int nreal, unsigned cm, Real ds, ScanF scan)
+{
+    constexpr int CAP = RowResult<Real, K>::CAP;
+    if (n < 32) cm &= (1u << n) - 1u;
+    int hi = 32;
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) {
+        if (m <= kk && m >= nreal) {
+            int cj = n;
+            if (cm) {
+                cj = lowest_bit(cm);
+                cm &= cm - 1;
+            } else {
+                for (; hi < n && cj == n; ++hi)
+                    if (!scan(hi)) cj = hi;
+            }
+            if (cj < n) { o.td[m] = ds; o.tj[m] = cj; }
+        }
+    }
+}
+
 // The same row from its segment of the evaluated work list (rollout kernel): ent[q] / res[q],
-// q < cnt, ascending j.  Real candidates (d < d_safety[i], self included) are sorted by
-// (d, j); the clipped agents all sit at exactly d_safety[i] behind them, so the free slots are
-// filled with the lowest clipped indices directly.
+// q < cnt, ascending j.
 template <typename Real, int K>
 DS_HD void eval_row_from_list(RowResult<Real, K> &o, int n, int i, Real xi, Real yi,
                               const AgentConst<Real> &c, const unsigned *__restrict__ ent,
@@ -543,57 +590,84 @@ DS_HD void eval_row_from_list(RowResult<Real, K> &o, int n, int i, Real xi, Real
     const int kk = (K >= 0) ? K : P.k;
 #pragma unroll
     for (int m = 0; m < CAP; ++m) { o.td[m] = real_inf<Real>(); o.tj[m] = 0; }
-    Real sum_local = 0, sum_all = 0;
-    int ncoll = 0, nreal = 0;
+    RowAcc<Real> acc;
+    acc.sum_local = 0; acc.sum_all = 0; acc.ncoll = 0;
+    int nreal = 0;
     // j == i (:323-325): dist = 0, d_ii = min(-2 l_i, d_safety[i]), d_norm = 1 -> no barrier term
     const Real raw_ii = sub_rn(sub_rn((Real)0, c.radius), c.radius);
     const Real d_ii = (c.ds < raw_ii) ? c.ds : raw_ii;
-    int cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);               // :328 deltas[j], j == i
-    const bool self_unclipped = (d_ii != c.ds);
-    if (d_ii < c.ds) { o.td[0] = d_ii; o.tj[0] = i; nreal = 1; }
-    unsigned unclipped_lo = (self_unclipped && i < 32) ? (1u << i) : 0u;   // agents j < 32 only
+    acc.cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);               // :328 deltas[j], j == i
+    acc.self_unclipped = (d_ii != c.ds);
+    unsigned unclipped_lo = (acc.self_unclipped && i < 32) ? (1u << i) : 0u;   // agents j < 32 only
     for (int q = 0; q < cnt; ++q) {
         const unsigned w = ent[q];
         const V2 dv = res[q];
         const int j = (int)(w & 1023u);
-        cnt_nd += (int)((w >> 12) & 3u) - 1;                            // replaces the clipped-pair count
-        if (dv.x != c.ds) {                                             // not clipped (NaN included)
-            if (j < 32) unclipped_lo |= 1u << j;
-            ncoll += (int)((w >> 11) & 1u);
-            sum_all = add_rn(sum_all, dv.y);                                                    // :283
-            sum_local = add_rn(sum_local, mul_rn(dv.y, ((w >> 10) & 1u) ? (Real)1 : (Real)0));  // :282
-            if (dv.x < c.ds) { topk_insert<Real, K>(o, dv.x, j); ++nreal; }
-        }
+        acc.cnt_nd += (int)((w >> 12) & 3u) - 1;                        // replaces the clipped-pair count
+        // a clipped pair carries logd = +0 and no collision flag: the sums take it unconditionally
+        const bool live = dv.x != c.ds;                                 // not clipped (NaN included)
+        unclipped_lo |= (live && j < 32) ? (1u << j) : 0u;
+        acc.ncoll += (int)((w >> 11) & 1u);
+        acc.sum_all = add_rn(acc.sum_all, dv.y);                                                    // :283
+        acc.sum_local = add_rn(acc.sum_local, mul_rn(dv.y, ((w >> 10) & 1u) ? (Real)1 : (Real)0));  // :282
+        const bool cand = dv.x < c.ds;                                  // real candidate for the k nearest
+        topk_insert_sorted<Real, K>(o, cand ? dv.x : real_inf<Real>(), j);
+        nreal += cand ? 1 : 0;
     }
-    // free slots <- lowest clipped indices (d = d_safety[i] for all of them: index order)
-    unsigned cm = ~unclipped_lo;
-    if (n < 32) cm &= (1u << n) - 1u;
-    int hi = 32;                                                        // next index to test when n > 32
-#pragma unroll
-    for (int m = 0; m < CAP; ++m) {
-        if (m <= kk && m >= nreal) {
-            int cj = n;
-            if (cm) {
-                cj = lowest_bit(cm);
-                cm &= cm - 1;
-            } else {
-                for (; hi < n && cj == n; ++hi) {                       // rare: >= 32 - k agents unclipped
-                    bool unclipped = (hi == i) && self_unclipped;
-                    for (int q = 0; q < cnt; ++q)
-                        if ((int)(ent[q] & 1023u) == hi && res[q].x != c.ds) unclipped = true;
-                    if (!unclipped) cj = hi;
-                }
-            }
-            if (cj < n) { o.td[m] = c.ds; o.tj[m] = cj; }
-        }
-    }
-    RowAcc<Real> acc;
-    acc.sum_local = sum_local; acc.sum_all = sum_all; acc.ncoll = ncoll; acc.cnt_nd = cnt_nd;
-    acc.self_unclipped = self_unclipped;
+    if (d_ii < c.ds) { topk_merge_self<Real, K>(o, d_ii, i); ++nreal; }
+    topk_fill_clipped<Real, K>(o, kk, n, nreal, ~unclipped_lo, c.ds, [&](int hi) {
+        bool unclipped = (hi == i) && acc.self_unclipped;
+        for (int q = 0; q < cnt; ++q)
+            if ((int)(ent[q] & 1023u) == hi && res[q].x != c.ds) unclipped = true;
+        return unclipped;
+    });
     row_end<Real, K>(o, acc, xi, yi, c, P);
 }
 
-// Write z_i (k+1 rows) and Ni_i (drone_env.py:344-397) for global agent index g.
+// The same row when n <= 32 and the row evaluates its own near pairs (dense small-n frames, where
+// a work list costs more than the imbalance it removes): `near` = pass-1 mask of the row.
+// cpair[j] = (radius_j, delta_j).
+template <typename Real, int K>
+DS_HD void eval_row_near32(RowResult<Real, K> &o, int n, int i, Real xi, Real yi, const AgentConst<Real> &c,
+                           unsigned near, const typename vec2_of<Real>::type *__restrict__ s_pos,
+                           const typename vec2_of<Real>::type *__restrict__ cpair, const ParamsR<Real> &P,
+                           const LogTabEntry *__restrict__ tab)
+{
+    using V2 = typename vec2_of<Real>::type;
+    constexpr int CAP = RowResult<Real, K>::CAP;
+    const int kk = (K >= 0) ? K : P.k;
+#pragma unroll
+    for (int m = 0; m < CAP; ++m) { o.td[m] = real_inf<Real>(); o.tj[m] = 0; }
+    RowAcc<Real> acc;
+    acc.sum_local = 0; acc.sum_all = 0; acc.ncoll = 0;
+    int nreal = 0;
+    const Real raw_ii = sub_rn(sub_rn((Real)0, c.radius), c.radius);   // j == i (:323-325)
+    const Real d_ii = (c.ds < raw_ii) ? c.ds : raw_ii;
+    acc.cnt_nd = c.clipcnt + ((d_ii <= c.delta) ? 1 : 0);
+    acc.self_unclipped = (d_ii != c.ds);
+    unsigned unclipped = acc.self_unclipped ? (1u << i) : 0u;
+    while (near) {                                                      // ascending j (:282-283)
+        const int j = lowest_bit(near);
+        near &= near - 1;
+        const V2 pj = s_pos[j], cj = cpair[j];
+        PairOut<Real> po;
+        eval_pair<Real>(po, xi, yi, pj.x, pj.y, c.ds, c.radius, cj.x, cj.y, c.log_ds, P, tab);
+        acc.cnt_nd += (po.in_disk ? 1 : 0) - ((c.ds <= cj.y) ? 1 : 0);
+        unclipped |= (po.d != c.ds) ? (1u << j) : 0u;
+        acc.ncoll += po.coll ? 1 : 0;
+        acc.sum_all = add_rn(acc.sum_all, po.logd);
+        acc.sum_local = add_rn(acc.sum_local, mul_rn(po.logd, po.in_disk ? (Real)1 : (Real)0));
+        const bool cand = po.d < c.ds;
+        topk_insert_sorted<Real, K>(o, cand ? po.d : real_inf<Real>(), j);
+        nreal += cand ? 1 : 0;
+    }
+    if (d_ii < c.ds) { topk_merge_self<Real, K>(o, d_ii, i); ++nreal; }
+    topk_fill_clipped<Real, K>(o, kk, n, nreal, ~unclipped, c.ds, [](int) { return true; });
+    row_end<Real, K>(o, acc, xi, yi, c, P);
+}
+
+// Write z_i (k+1 rows) and Ni_i (drone_env.py:344-397) for global agent index g.  The in-range
+// neighbours occupy slots 1..min(in_range, k) in order, so Ni[kth] is either tj[kth] or -1.
 template <typename Real, int K>
 DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
                      const AgentConst<Real> &c,
@@ -608,9 +682,12 @@ DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
     constexpr int CAP = RowResult<Real, K>::CAP;
     int *nl = Ni + g * (size_t)(kk + 1);
     nl[0] = i;
-    int nn = 1;
     Real ghx = 0, ghy = 0;
-    bool ghost_ready = false;
+    if (o.in_range < kk) {                                            // ghost rows (:383-386)
+        const Real zn = sqrt_rn(fma_rn(o.zy, o.zy, mul_rn(o.zx, o.zx)));
+        ghx = mul_rn(mul_rn(div_rn(o.zx, zn), c.delta), P.ghost);
+        ghy = mul_rn(mul_rn(div_rn(o.zy, zn), c.delta), P.ghost);
+    }
     if (P.simplify) {
         V2 *zr = reinterpret_cast<V2 *>(z + g * (size_t)(kk + 1) * 2);
         V2 v; v.x = o.zx; v.y = o.zy;
@@ -619,20 +696,12 @@ DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
         for (int kth = 1; kth < CAP; ++kth) {
             if (kth <= kk) {
                 const int j = o.tj[kth];
-                if (kth <= o.in_range) {                              // :362-368
-                    const V2 pj = s_pos[j];
-                    v.x = sub_rn(pj.x, xi); v.y = sub_rn(pj.y, yi);
-                    nl[nn++] = j;
-                } else {                                              // :383-386
-                    if (!ghost_ready) {
-                        const Real zn = sqrt_rn(fma_rn(o.zy, o.zy, mul_rn(o.zx, o.zx)));
-                        ghx = mul_rn(mul_rn(div_rn(o.zx, zn), c.delta), P.ghost);
-                        ghy = mul_rn(mul_rn(div_rn(o.zy, zn), c.delta), P.ghost);
-                        ghost_ready = true;
-                    }
-                    v.x = ghx; v.y = ghy;
-                }
+                const bool in_r = kth <= o.in_range;                  // :362-368
+                const V2 pj = s_pos[j];
+                v.x = in_r ? sub_rn(pj.x, xi) : ghx;
+                v.y = in_r ? sub_rn(pj.y, yi) : ghy;
                 zr[kth] = v;
+                nl[kth] = in_r ? j : -1;
             }
         }
     } else {
@@ -643,27 +712,17 @@ DS_HD void write_obs(const RowResult<Real, K> &o, int i, Real xi, Real yi,
         for (int kth = 1; kth < CAP; ++kth) {
             if (kth <= kk) {
                 const int j = o.tj[kth];
-                Real a, bq;
-                if (kth <= o.in_range) {
-                    const V2 pj = s_pos[j];
-                    a = sub_rn(pj.x, xi); bq = sub_rn(pj.y, yi);
-                    nl[nn++] = j;
-                } else {
-                    if (!ghost_ready) {
-                        const Real zn = sqrt_rn(fma_rn(o.zy, o.zy, mul_rn(o.zx, o.zx)));
-                        ghx = mul_rn(mul_rn(div_rn(o.zx, zn), c.delta), P.ghost);
-                        ghy = mul_rn(mul_rn(div_rn(o.zy, zn), c.delta), P.ghost);
-                        ghost_ready = true;
-                    }
-                    a = ghx; bq = ghy;
-                }
+                const bool in_r = kth <= o.in_range;
+                const V2 pj = s_pos[j];
                 const V2 vj = s_vel[j];                               // zj = state[j,:].copy() (:367,385)
                 Real *row = zr + kth * 5;
-                row[0] = a; row[1] = bq; row[2] = vj.x; row[3] = vj.y; row[4] = s_radius[j * cs];
+                row[0] = in_r ? sub_rn(pj.x, xi) : ghx;
+                row[1] = in_r ? sub_rn(pj.y, yi) : ghy;
+                row[2] = vj.x; row[3] = vj.y; row[4] = s_radius[j * cs];
+                nl[kth] = in_r ? j : -1;
             }
         }
     }
-    for (; nn <= kk; ++nn) nl[nn] = -1;
 }
 
 #if defined(__CUDACC__)
@@ -766,10 +825,10 @@ step_kernel(const StepArgs a)
 
 // ---------------------------------------------------------------- rollout kernel
 // Shared memory of a rollout CTA.  Per CTA: constants [n], log table, work list [L].  Per row
-// (I = TC*G*n), double buffered over chunks: action, position; single: r, true_r.  Per agent of
-// a slice (A = G*n): chunk start position, last executed velocity.  Per frame (F = TC*G):
-// collision count, not-at-goal flag, frame info, per-frame means.  Per environment (G): alive,
-// t, executed slices of the chunk.
+// (I = TC*G*n), double buffered over chunks: action, position.  Per agent of a slice
+// (A = G*n): final position / velocity.  Per frame (F = TC*G): collision count.  Per
+// environment (G): bit s of ngbits = "slice s has an agent that is not at its goal"; alive and t
+// per chunk parity.
 template <typename Real> struct RoSmem {
     using V2 = typename vec2_of<Real>::type;
     V2 *cA;                  // [n] (d_safety, log d_safety)
@@ -777,11 +836,10 @@ template <typename Real> struct RoSmem {
     V2 *cF;                  // [n] end point
     LogTabEntry *logtab;
     V2 *act_, *pos_, *p0, *vfin, *res;   // act_ / pos_: two buffers of I rows (chunk parity)
-    int I_, G_;
-    Real *r, *tr;
     unsigned *ent;
-    double *mr, *mtr;
-    int *cnt, *notgoal, *finfo, *alive_, *tenv_, *nexec, *lcount;   // alive_ / tenv_: per chunk parity
+    int I_, G_;
+    int *cnt, *alive_, *tenv_, *lcount;  // alive_ / tenv_: per chunk parity
+    unsigned *ngbits;
     __device__ V2 *act(int b) const { return act_ + b * I_; }
     __device__ V2 *pos(int b) const { return pos_ + b * I_; }
     __device__ int *alive(int b) const { return alive_ + b * G_; }
@@ -791,50 +849,87 @@ template <typename Real> struct RoSmem {
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
         return (3 * (size_t)n + 4 * I + 2 * A + (size_t)L) * sizeof(V2) + kLogTabSize * sizeof(LogTabEntry) +
-               align16(2 * I * sizeof(Real)) + align16((size_t)L * sizeof(unsigned)) + 2 * F * sizeof(double) +
-               align16(3 * F * sizeof(int)) + align16((5 * (size_t)G + 1) * sizeof(int));
+               align16((size_t)L * sizeof(unsigned)) + align16(F * sizeof(int)) +
+               align16((5 * (size_t)G + 1) * sizeof(int));
     }
     __device__ RoSmem(unsigned char *base, int n, int G, int TC, int L)
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
         unsigned char *p = base;
-        cA = reinterpret_cast<V2 *>(p); cB = cA + n; cF = cB + n;
         I_ = (int)I; G_ = G;
+        cA = reinterpret_cast<V2 *>(p); cB = cA + n; cF = cB + n;
         act_ = cF + n; pos_ = act_ + 2 * I;
         p0 = pos_ + 2 * I; vfin = p0 + A; res = vfin + A;
         p += (3 * (size_t)n + 4 * I + 2 * A + (size_t)L) * sizeof(V2);
         logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);
-        r = reinterpret_cast<Real *>(p); tr = r + I; p += align16(2 * I * sizeof(Real));
         ent = reinterpret_cast<unsigned *>(p); p += align16((size_t)L * sizeof(unsigned));
-        mr = reinterpret_cast<double *>(p); mtr = mr + F; p += 2 * F * sizeof(double);
-        cnt = reinterpret_cast<int *>(p); notgoal = cnt + F; finfo = notgoal + F; p += align16(3 * F * sizeof(int));
-        alive_ = reinterpret_cast<int *>(p); tenv_ = alive_ + 2 * G; nexec = tenv_ + 2 * G; lcount = nexec + G;
+        cnt = reinterpret_cast<int *>(p); p += align16(F * sizeof(int));
+        alive_ = reinterpret_cast<int *>(p); tenv_ = alive_ + 2 * G;
+        ngbits = reinterpret_cast<unsigned *>(tenv_ + 2 * G); lcount = tenv_ + 3 * G;
     }
 };
+
+// Pass 1 over one block of <= 32 agents of the row's frame: bit jj of the result = pair
+// (i, j0 + jj) is NOT provably clipped.  near <=> !(d2 >= thr2) <=> the sign bit of thr2 - d2 is
+// clear (+0 and NaN count as near: the exact path is always right), shifted into the mask with
+// one funnel shift per pair.
+__device__ __forceinline__ int sign_word(double t) { return __double2hiint(t); }
+__device__ __forceinline__ int sign_word(float t) { return __float_as_int(t); }
+template <typename Real>
+__device__ __forceinline__ unsigned pass1_block(const typename vec2_of<Real>::type *__restrict__ fp, int jn,
+                                                Real px, Real py, Real thr2)
+{
+    using V2 = typename vec2_of<Real>::type;
+    unsigned m = 0;
+#pragma unroll 4
+    for (int jj = 0; jj < jn; ++jj) {
+        const V2 pj = fp[jj];
+        const Real dx = sub_rn(px, pj.x), dy = sub_rn(py, pj.y);
+        const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
+        m = __funnelshift_l((unsigned)sign_word(sub_rn(thr2, d2)), m, 1);   // m = m << 1 | sign
+    }
+    // m: NOT-near bits, agent jj at bit jn - 1 - jj
+    return __brev(~m) >> (32 - jn);
+}
 
 #ifndef DS_RO_MINB
 #define DS_RO_MINB 2      // CTAs of 256 threads per SM the rollout kernel is compiled for (register cap)
 #endif
-// frame info word written by the frame's leader thread after the rows are evaluated
-constexpr int kFrameExec = 1, kFrameFin = 2, kFrameLast = 4;
 
-// T fused steps, TC time slices per chunk evaluated concurrently (see the header comment).
+// Which slices of a chunk execute (drone_env.py:248-256): the episode ends at the first slice
+// whose agents are all at their goals (bit clear in ngbits) or whose t reaches max_steps - 1.
+// Returns the number of executed slices; *env_fin = the last of them finished the episode.
+DS_HD int executed_slices(unsigned ngbits, int tt, int nsl, int max_steps, bool *env_fin)
+{
+    const unsigned full = (nsl >= 32) ? 0xffffffffu : ((1u << nsl) - 1u);
+    const unsigned atgoal = ~ngbits & full;
+    const int fg = atgoal ? lowest_bit(atgoal) : nsl;        // first slice with everybody at goal
+    int ft = max_steps - 1 - tt;                             // first slice at the time limit
+    ft = ft < 0 ? 0 : ft;
+    const int first = fg < ft ? fg : ft;
+    *env_fin = first < nsl;
+    return *env_fin ? first + 1 : nsl;
+}
+
+// T fused steps, TC <= 32 time slices per chunk evaluated concurrently (see the header comment).
 // NB = number of 32-agent blocks whose near masks a row keeps in registers (n <= 32 NB);
 // NB == 0: any n, masks in local memory.  Element indices are 32 bit: the host splits a call
 // whose T * E * n would not fit.
 //
-// Staging of chunk c (buffer c & 1), overlapped with the tail of chunk c - 1: the rows put their
-// prefetched actions into act[], then one thread per agent integrates through the chunk's slices
-// (sequential, bit-exact: A = I, B = dt I, drone_env.py:78-79,235) into pos[].
-// One chunk, five barriers:
+// Positions of chunk c + 1 are produced during chunk c by one thread per agent: sequential,
+// bit-exact single-integrator steps (A = I, B = dt I, drone_env.py:78-79,235) continuing from the
+// LAST slice of chunk c.  That is speculative only in appearance: if the episode ends inside
+// chunk c the environment stops stepping and the positions are never looked at.
+// One chunk, four barriers:
 //   (c) every row: pass 1 over its frame -> near masks; a warp scan + one smem atomic per warp
-//       gives the row a contiguous segment of the work list; entries written          | barrier
-//   (d) all threads: one near pair per thread per round (eval_pair)                   | barrier
-//   (e) every row folds its segment, finishes the row, posts r / true_r / collision count /
-//       not-at-goal to its frame; actions of the next chunk -> act[]                  | barrier
-//   (f) threads < F: leader of one frame each -- executed?, finished?, frame means    | barrier
-//   (g) every executed row stores its outputs; threads < G accumulate the episode sums and
-//       advance t / alive; threads < A integrate the next chunk                       | barrier
+//       gives the row a contiguous segment of the work list; entries written; the prefetched
+//       actions of chunk c + 1 -> act[]                                               | barrier
+//   (d) all threads: one near pair per thread per round (eval_pair); threads < A integrate
+//       chunk c + 1                                                                   | barrier
+//   (e) every row folds its segment and finishes the row; collision count and not-at-goal bit
+//       posted to its frame / environment                                             | barrier
+//   (g) every row of an executed slice stores its outputs and adds to its running episode sums;
+//       one thread per environment advances t / alive                                 | barrier
 template <typename Real, int K, int NT, int NB>
 __global__ void __launch_bounds__(NT, (NT <= 256) ? DS_RO_MINB : 1)
 rollout_kernel(const RolloutArgs ra)
@@ -853,9 +948,7 @@ rollout_kernel(const RolloutArgs ra)
     if (sizeof(Real) == 8)
         for (int idx = threadIdx.x; idx < kLogTabSize; idx += blockDim.x) sm.logtab[idx] = a.c.logtab[idx];
     const ParamsR<Real> P(a);
-    const int kk = (K >= 0) ? K : a.k;
     const int A = G * n;                              // agents per slice in this CTA
-    const int F = G * TC;                             // frames per chunk in this CTA
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int s = tid / A, ag = tid - s * A;          // time slice within the chunk, agent slot
@@ -869,29 +962,29 @@ rollout_kernel(const RolloutArgs ra)
     const Real thr2 = active ? ((const Real *)a.c.thr2)[i] : (Real)0;
     const int clipcnt = active ? a.c.clipcnt[i] : 0;
     const bool agent_thread = tid < A && e < E;       // s == 0: owns agent ag across the call
+    const bool env_thread = agent_thread && i == 0;   // owns environment le across the call
+    // lanes of this warp that hold rows of the same frame; the first of them posts for the frame
+    unsigned fmask;
+    {
+        const int lo = (lane - i > 0) ? lane - i : 0, hi = (lane + (n - 1 - i) < 31) ? lane + (n - 1 - i) : 31;
+        fmask = ((hi - lo == 31) ? 0xffffffffu : ((1u << (hi - lo + 1)) - 1u)) << lo;
+    }
+    const bool frame_poster = (i == 0 || lane == 0);
 
     if (agent_thread) {
         sm.p0[tid] = reinterpret_cast<const V2 *>(a.pos)[g];
         sm.vfin[tid] = reinterpret_cast<const V2 *>(a.vel)[g];
         if (i == 0) { sm.alive(0)[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv(0)[le] = a.t[e]; }
     }
-    // per-environment episode accumulators live in thread le (< G)
-    const int e_acc = blockIdx.x * G + tid;
-    const bool acc_thread = tid < G && e_acc < E;
-    double acc_r = 0, acc_tr = 0, acc_c = 0, acc_s = 0;
-    if (acc_thread) {
-        const double *ag4 = ra.agg + (size_t)e_acc * 4;
-        acc_r = ag4[0]; acc_tr = ag4[1]; acc_c = ag4[2]; acc_s = ag4[3];
-    }
-    bool stepped = false;
+    Real sum_r = 0, sum_tr = 0;                       // this row's share of the episode sums
+    int sum_c = 0, steps = 0;                         // i == 0 rows: collisions; env thread: steps
 
     auto load_action = [&](unsigned at) -> V2 {
         if (ra.actions) return reinterpret_cast<const V2 *>(ra.actions)[at];
         return atab[ra.aidx[at]];
     };
-    // sequential integration of one agent through the nsl slices of a chunk
-    auto integrate = [&](int buf, int nsl) {
-        V2 p = sm.p0[tid];
+    // sequential integration of agent `tid` through nsl slices: pos(buf)[q] = start + dt u_0 .. u_q
+    auto integrate = [&](V2 p, int buf, int nsl) {
         const V2 *ua = sm.act(buf) + tid;
         V2 *pa = sm.pos(buf) + tid;
         for (int q = 0; q < nsl; ++q) {
@@ -903,43 +996,40 @@ rollout_kernel(const RolloutArgs ra)
     };
     unsigned at = (unsigned)s * EN + g;               // element index of this row at slice t0 + s
     unsigned fe = (unsigned)s * E + (unsigned)e;
-    V2 u{}, u_next{};
-    if (active && s < T) u = load_action(at);
+    // stage chunk 0; u_next always holds the prefetched action of the NEXT chunk's slice
+    V2 u_next{};
+    if (active && s < T) sm.act(0)[tid] = load_action(at);
     if (active && TC + s < T) u_next = load_action(at + (unsigned)TC * EN);
-    // stage chunk 0
-    if (active && s < T) sm.act(0)[tid] = u;
     if (tid == 0) *sm.lcount = 0;
     __syncthreads();
-    if (agent_thread && sm.alive(0)[le] != 0) integrate(0, (T < TC) ? T : TC);
+    if (agent_thread && sm.alive(0)[le] != 0) integrate(sm.p0[tid], 0, (T < TC) ? T : TC);
     __syncthreads();
 
+    // dense small-n frames: every row evaluates its own near pairs, two barriers per chunk
+    const bool inl = (NB == 1) && ra.inline_rows != 0;
     for (int t0 = 0, buf = 0; t0 < T; t0 += TC, buf ^= 1) {
         const int nsl = (T - t0 < TC) ? (T - t0) : TC;      // slices in this chunk
         const bool in_chunk = active && s < nsl;
+        const bool env_alive = active && sm.alive(buf)[le] != 0;
+        const bool valid = in_chunk && env_alive;
+        const bool more = t0 + TC < T;                       // there is a chunk after this one
         // (c) pass 1
-        const bool valid = in_chunk && sm.alive(buf)[le] != 0;
         V2 p{};
         constexpr int NBR = (NB > 0) ? NB : 32;
         unsigned near[NBR];
         int ncnt = 0;
         const V2 *fpos = sm.pos(buf) + (tid - i);           // positions of this row's frame
+        if (env_thread) sm.ngbits[le] = 0;
         if (valid) {
             p = fpos[i];
-            if (i == 0) { sm.cnt[fr] = 0; sm.notgoal[fr] = 0; }
+            if (i == 0) sm.cnt[fr] = 0;
             if (NB > 0) {
 #pragma unroll
                 for (int bk = 0; bk < NBR; ++bk) {
                     const int j0 = bk * 32;
                     unsigned m = 0;
                     if (j0 < n) {
-                        const int jn = (n - j0 < 32) ? (n - j0) : 32;
-#pragma unroll 4
-                        for (int jj = 0; jj < jn; ++jj) {
-                            const V2 pj = fpos[j0 + jj];
-                            const Real dx = sub_rn(p.x, pj.x), dy = sub_rn(p.y, pj.y);
-                            const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
-                            m |= ((d2 >= thr2) ? 0u : 1u) << jj;            // NaN -> near (exact path)
-                        }
+                        m = pass1_block<Real>(fpos + j0, (n - j0 < 32) ? (n - j0) : 32, p.x, p.y, thr2);
                         if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
                     }
                     near[bk] = m;
@@ -947,15 +1037,7 @@ rollout_kernel(const RolloutArgs ra)
                 }
             } else {
                 for (int j0 = 0, bk = 0; j0 < n; j0 += 32, ++bk) {
-                    const int jn = (n - j0 < 32) ? (n - j0) : 32;
-                    unsigned m = 0;
-#pragma unroll 4
-                    for (int jj = 0; jj < jn; ++jj) {
-                        const V2 pj = fpos[j0 + jj];
-                        const Real dx = sub_rn(p.x, pj.x), dy = sub_rn(p.y, pj.y);
-                        const Real d2 = fma_rn(dy, dy, mul_rn(dx, dx));
-                        m |= ((d2 >= thr2) ? 0u : 1u) << jj;
-                    }
+                    unsigned m = pass1_block<Real>(fpos + j0, (n - j0 < 32) ? (n - j0) : 32, p.x, p.y, thr2);
                     if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
                     near[bk] = m;
                     ncnt += __popc(m);
@@ -963,38 +1045,45 @@ rollout_kernel(const RolloutArgs ra)
             }
         }
         // segment of the work list: exclusive scan over the warp, one atomic per warp
-        int incl = ncnt;
+        int seg = 0;
+        bool listed = true;
+        if (!inl) {
+            int incl = ncnt;
 #pragma unroll
-        for (int w = 1; w < 32; w <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, w);
-            if (lane >= w) incl += v;
-        }
-        int wbase = 0;
-        if (lane == 31 && incl > 0) wbase = atomicAdd(sm.lcount, incl);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        const int seg = wbase + incl - ncnt;
-        const bool listed = ncnt == 0 || seg + ncnt <= L;    // otherwise the row evaluates itself in (e)
-        if (valid && ncnt > 0) {
-            unsigned *ep = sm.ent + seg;
-            if (listed) {
-                const unsigned base = (unsigned)tid | ((unsigned)i << 20);
-                const int nb = (NB > 0) ? NBR : (n + 31) / 32;
+            for (int w = 1; w < 32; w <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, w);
+                if (lane >= w) incl += v;
+            }
+            int wbase = 0;
+            if (lane == 31 && incl > 0) wbase = atomicAdd(sm.lcount, incl);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            seg = wbase + incl - ncnt;
+            listed = ncnt == 0 || seg + ncnt <= L;           // otherwise the row evaluates itself in (e)
+            if (valid && ncnt > 0) {
+                unsigned *ep = sm.ent + seg;
+                if (listed) {
+                    const unsigned base = (unsigned)tid | ((unsigned)i << 20);
+                    const int nb = (NB > 0) ? NBR : (n + 31) / 32;
 #pragma unroll
-                for (int bk = 0; bk < nb; ++bk) {
-                    unsigned m = near[bk];
-                    while (m) {
-                        const int jj = lowest_bit(m);
-                        m &= m - 1;
-                        *ep++ = base | ((unsigned)(bk * 32 + jj) << 10);
+                    for (int bk = 0; bk < nb; ++bk) {
+                        unsigned m = near[bk];
+                        while (m) {
+                            const int jj = lowest_bit(m);
+                            m &= m - 1;
+                            *ep++ = base | ((unsigned)(bk * 32 + jj) << 10);
+                        }
                     }
+                } else {
+                    for (int q = seg; q < L && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
                 }
-            } else {
-                for (int q = seg; q < L && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
             }
         }
-        __syncthreads();
+        // actions of the next chunk (integrated in (d)); prefetch the chunk after it
+        if (active && t0 + TC + s < T) sm.act(buf ^ 1)[tid] = u_next;
+        if (active && t0 + 2 * TC + s < T) u_next = load_action(at + 2u * (unsigned)TC * EN);
+        if (!inl) __syncthreads();
         // (d) pass 2: one near pair per thread per round
-        {
+        if (!inl) {
             const int M = (*sm.lcount < L) ? *sm.lcount : L;
             for (int q = tid; q < M; q += blockDim.x) {
                 const unsigned w = sm.ent[q];
@@ -1009,60 +1098,51 @@ rollout_kernel(const RolloutArgs ra)
                 sm.ent[q] = pack_result(j, po.in_disk, po.coll, (po.in_disk ? 1 : 0) - ((ca.x <= cbj.y) ? 1 : 0) + 1);
             }
         }
-        __syncthreads();
+        if (!inl) {
+            if (agent_thread && more && env_alive)
+                integrate(sm.pos(buf)[(TC - 1) * A + tid], buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
+            __syncthreads();
+        }
         // (e) rows
         RowResult<Real, K> o;
-        AgentConst<Real> c;
+        bool notgoal = false;
         if (valid) {
+            AgentConst<Real> c;
             const V2 ca = sm.cA[i], cb = sm.cB[i], cf = sm.cF[i];
             c.xF = cf.x; c.yF = cf.y; c.ds = ca.x; c.log_ds = ca.y; c.radius = cb.x; c.delta = cb.y;
             c.thr2 = thr2; c.clipcnt = clipcnt;
-            if (listed)
+            if (inl)
+                eval_row_near32<Real, K>(o, n, i, p.x, p.y, c, near[0], fpos, sm.cB, P, sm.logtab);
+            else if (listed)
                 eval_row_from_list<Real, K>(o, n, i, p.x, p.y, c, sm.ent + seg, sm.res + seg, ncnt, P);
             else
                 eval_row<Real, K>(o, n, i, p.x, p.y, c, fpos, &sm.cB[0].y, &sm.cB[0].x, P, sm.logtab, 2);
-            sm.r[tid] = o.r;
-            sm.tr[tid] = o.tr;
             if (o.ncoll) atomicAdd(&sm.cnt[fr], o.ncoll);
-            if (!o.at_goal) sm.notgoal[fr] = 1;
+            notgoal = !o.at_goal;
+        }
+        {
+            // one atomic per (frame, warp): any row of the frame in this warp not at its goal
+            const unsigned bal = __ballot_sync(0xffffffffu, notgoal);
+            if (frame_poster && active && (bal & fmask)) atomicOr(&sm.ngbits[le], 1u << s);
         }
         if (tid == 0) *sm.lcount = 0;                        // every thread has read it in (d)
-        // actions of the next chunk (read by the integration in (g), after two more barriers)
-        if (active && t0 + TC + s < T) sm.act(buf ^ 1)[tid] = u_next;
         __syncthreads();
-        // (f) frame leaders: a slice executes iff no earlier slice of this chunk finished the
-        // episode (:248-256); frame means for the episode sums (train_problem.py:98-100)
-        if (tid < F) {
-            const int fs = tid / G, fle = tid - fs * G;      // slice, local environment of frame tid
-            int info = 0;
-            if (blockIdx.x * G + fle < E && fs < nsl && sm.alive(buf)[fle] != 0) {
-                const int ft0 = sm.tenv(buf)[fle];
-                bool exec = true;
-                for (int q = 0; q < fs; ++q)
-                    if (sm.notgoal[q * G + fle] == 0 || ft0 + q >= a.max_steps - 1) exec = false;
-                if (exec) {
-                    const bool fin = (sm.notgoal[tid] == 0) || (ft0 + fs >= a.max_steps - 1);
-                    const bool last = fin || (fs == nsl - 1);        // last executed slice of this chunk
-                    info = kFrameExec | (fin ? kFrameFin : 0) | (last ? kFrameLast : 0);
-                    double sr = 0, st = 0;
-                    const Real *rr = sm.r + fs * A + fle * n, *rt = sm.tr + fs * A + fle * n;
-                    for (int j = 0; j < n; ++j) { sr += (double)rr[j]; st += (double)rt[j]; }
-                    sm.mr[tid] = sr / n; sm.mtr[tid] = st / n;
-                    if (last) sm.nexec[fle] = fs + 1 + (fin ? 0x10000 : 0);
-                }
-            }
-            sm.finfo[tid] = info;
-        }
-        __syncthreads();
+        // inline mode: the next chunk's actions are staged by now; integrate here
+        if (inl && agent_thread && more && env_alive)
+            integrate(sm.pos(buf)[(TC - 1) * A + tid], buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
         // (g) stores
+        int ne = 0;
+        bool env_fin = false;
+        if (env_alive) ne = executed_slices(sm.ngbits[le], sm.tenv(buf)[le], nsl, a.max_steps, &env_fin);
         if (valid) {
-            const int info = sm.finfo[fr];
-            if (info & kFrameExec) {
+            if (s < ne) {
                 const int nc = sm.cnt[fr];
-                const bool fin = (info & kFrameFin) != 0;
+                const bool fin = env_fin && s == ne - 1;
                 const V2 *fvel = sm.act(buf) + (tid - i);
+                AgentConst<Real> c{};
+                { const V2 cb = sm.cB[i]; c.radius = cb.x; c.delta = cb.y; }
                 if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
-                if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = u;              // :238
+                if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = fvel[i];        // :238
                 if (ra.r_tr) reinterpret_cast<Real *>(ra.r_tr)[at] = o.r;
                 if (ra.tr_tr) reinterpret_cast<Real *>(ra.tr_tr)[at] = o.tr;
                 if (ra.z_tr)
@@ -1076,7 +1156,9 @@ rollout_kernel(const RolloutArgs ra)
                                        reinterpret_cast<Real *>(a.z), a.Ni, g, 2);
                     if (i == 0) { a.ncoll[e] = nc; a.fin[e] = fin ? 1 : 0; }
                 }
+                sum_r = add_rn(sum_r, o.r); sum_tr = add_rn(sum_tr, o.tr);
                 if (i == 0) {
+                    sum_c += nc;
                     if (ra.ncoll_tr) ra.ncoll_tr[fe] = nc;
                     if (ra.fin_tr) ra.fin_tr[fe] = fin ? 1 : 0;
                 }
@@ -1086,47 +1168,45 @@ rollout_kernel(const RolloutArgs ra)
         } else if (in_chunk && i == 0 && ra.fin_tr) {
             ra.fin_tr[fe] = 2;
         }
-        // one thread per agent: state after the chunk's last executed slice; next chunk's positions
-        if (agent_thread && sm.alive(buf)[le] != 0) {
-            const int ne = sm.nexec[le] & 0xffff;
+        // one thread per agent: state after the last executed slice, when the call ends here
+        if (agent_thread && env_alive && (env_fin || !more)) {
             sm.p0[tid] = sm.pos(buf)[(ne - 1) * A + tid];
             sm.vfin[tid] = sm.act(buf)[(ne - 1) * A + tid];
-            if (!(sm.nexec[le] & 0x10000) && t0 + TC < T)
-                integrate(buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
         }
-        // episode sums of this chunk, in time order; t / alive of the next chunk (other parity)
-        if (acc_thread) {
-            int ne = 0;
-            bool env_fin = false;
-            const bool was_alive = sm.alive(buf)[tid] != 0;
-            if (was_alive) {
-                ne = sm.nexec[tid] & 0xffff;
-                env_fin = (sm.nexec[tid] & 0x10000) != 0;
-                for (int q = 0; q < ne; ++q) {
-                    acc_r += sm.mr[q * G + tid]; acc_tr += sm.mtr[q * G + tid];
-                    acc_c += (double)sm.cnt[q * G + tid]; acc_s += 1;
-                }
-                stepped = true;
-            }
-            sm.tenv(buf ^ 1)[tid] = sm.tenv(buf)[tid] + ne;
-            sm.alive(buf ^ 1)[tid] = (was_alive && !env_fin) ? 1 : 0;
+        // one thread per environment: t / alive of the next chunk (other parity)
+        if (env_thread) {
+            steps += ne;
+            sm.tenv(buf ^ 1)[le] = sm.tenv(buf)[le] + ne;
+            sm.alive(buf ^ 1)[le] = (env_alive && !env_fin) ? 1 : 0;
         }
-        u = u_next;
         at += (unsigned)TC * EN; fe += (unsigned)TC * E;
-        if (active && t0 + 2 * TC + s < T) u_next = load_action(at + (unsigned)TC * EN);   // prefetch
         __syncthreads();
     }
     const int fbuf = ((T + TC - 1) / TC) & 1;                // parity the last chunk wrote
+    // episode sums (train_problem.py:98-100): sum over the call of mean_i r, mean_i true_r, the
+    // collision counts and the steps, reduced per environment in a fixed order
+    if (active) {
+        V2 v; v.x = sum_r; v.y = sum_tr;
+        sm.res[tid] = v;                                     // L >= I rows
+        sm.ent[tid] = (unsigned)sum_c;
+    }
+    __syncthreads();
     if (agent_thread) {
         reinterpret_cast<V2 *>(a.pos)[g] = sm.p0[tid];
         reinterpret_cast<V2 *>(a.vel)[g] = sm.vfin[tid];
     }
-    if (acc_thread) {
-        a.t[e_acc] = sm.tenv(fbuf)[tid];
-        if (stepped) {
-            if (sm.alive(fbuf)[tid] == 0) ra.done[e_acc] = 1;
-            double *ag4 = ra.agg + (size_t)e_acc * 4;
-            ag4[0] = acc_r; ag4[1] = acc_tr; ag4[2] = acc_c; ag4[3] = acc_s;
+    if (env_thread) {
+        a.t[e] = sm.tenv(fbuf)[le];
+        if (steps > 0) {
+            if (sm.alive(fbuf)[le] == 0) ra.done[e] = 1;
+            double sr = 0, st = 0, sc = 0;
+            for (int q = 0; q < TC; ++q) {
+                const V2 *rv = sm.res + q * A + le * n;
+                for (int j = 0; j < n; ++j) { sr += (double)rv[j].x; st += (double)rv[j].y; }
+                sc += (double)(int)sm.ent[q * A + le * n];
+            }
+            double *ag4 = ra.agg + (size_t)e * 4;
+            ag4[0] += sr / n; ag4[1] += st / n; ag4[2] += sc; ag4[3] += (double)steps;
         }
     }
 }

@@ -2,7 +2,8 @@
 // path eval_pair + eval_row_from_list, write_obs: the __host__ __device__ part) on the CPU for one
 // frame, so that the near/clipped split, the Delta-disk count and the k-nearest selection can be
 // checked against the oracle without a GPU.  path = 0: whole row in one call (step kernel);
-// path = 1: near pairs through a work list exactly as the rollout kernel lays them out.
+// path = 1: near pairs through a work list exactly as the rollout kernel lays them out;
+// path = 2: the rollout kernel's inline mode for n <= 32.
 // Never linked into libdronestep.so; the product has no CPU path.
 #include "../../scalable_collision_avoidance_rl_b200/csrc/dronestep_kernels.cuh"
 #include <vector>
@@ -32,7 +33,9 @@ static void run(int path, int n, int k, int simplify, int log_mode, const double
         double t2 = INFINITY;
         if (cds[i] != (Real)0 && std::isfinite(D) && D > 1e-6) { const double thr = D * (1 + m) + m; t2 = thr * thr * (1 + m); }
         cthr[i] = (Real)t2;
-        if (!(cthr[i] >= t2)) cthr[i] = (Real)INFINITY;
+        if (!(cthr[i] >= t2))
+            cthr[i] = (sizeof(Real) == 8) ? (Real)std::nextafter((double)cthr[i], (double)INFINITY)
+                                          : (Real)std::nextafterf((float)cthr[i], INFINITY);
         int cc = 0;
         for (int j = 0; j < n; ++j) if (j != i && cds[i] <= cdl[j]) ++cc;
         clip[i] = cc;
@@ -53,6 +56,18 @@ static void run(int path, int n, int k, int simplify, int log_mode, const double
         ds::RowResult<Real, K> o;
         if (path == 0) {
             ds::eval_row<Real, K>(o, n, i, sp[i].x, sp[i].y, c, sp.data(), cdl.data(), crd.data(), P, tab.data());
+        } else if (path == 2) {
+            // rollout kernel, inline mode (n <= 32): pass-1 mask, then the row folds its own near pairs
+            unsigned near = 0;
+            std::vector<V2> cpair(n);
+            for (int j = 0; j < n; ++j) {
+                cpair[j].x = crd[j]; cpair[j].y = cdl[j];
+                if (j == i) continue;
+                const Real dx = sp[i].x - sp[j].x, dy = sp[i].y - sp[j].y;
+                const Real d2 = ds::fma_rn(dy, dy, dx * dx);
+                if (!(d2 >= c.thr2)) near |= 1u << j;
+            }
+            ds::eval_row_near32<Real, K>(o, n, i, sp[i].x, sp[i].y, c, near, sp.data(), cpair.data(), P, tab.data());
         } else {
             // rollout kernel phases (c) -> (d) -> (e) for this row
             std::vector<unsigned> ent;

@@ -239,7 +239,8 @@ def test_host_entries_match_device_entries():
         torch.cuda.synchronize()
         for key in ("pos", "vel", "reward", "true_reward", "z", "Ni", "ncoll", "finished"):
             assert torch.equal(hb[key], da[key].cpu()), f"{key} chunk={chunk}"
-        assert torch.equal(hb["agg"], da["agg"].cpu())
+        # episode sums are reduced per call (rows first, then agents): chunking only reorders additions
+        assert_close(hb["agg"].numpy(), da["agg"].cpu().numpy(), FP64_TOL, f"agg chunk={chunk}")
 
 
 @pytest.mark.parametrize("n,grid,delta", [(10, [5, 5], 1.0), (32, [32, 32], 2.5)])
