@@ -45,7 +45,7 @@ struct ds_handle {
     int ro_L, ro_NB;          // work-list capacity; near-mask words kept in registers (0 = any n)
     int ro_inline;            // n <= 32: rows evaluate their own near pairs instead of the work list
     size_t ro_smem;
-    size_t smem_optin;
+    size_t smem_optin, smem_sm;
     // device constants (Real typed unless noted)
     void *d_xF, *d_ds, *d_delta, *d_radius, *d_logds, *d_thr2;
     int *d_clipcnt;
@@ -146,10 +146,14 @@ size_t rollout_smem(const ds_handle *h, int G, int TC, int L)
     return h->real_bytes == 8 ? ds::RoSmem<double>::bytes(h->n, G, TC, L) : ds::RoSmem<float>::bytes(h->n, G, TC, L);
 }
 
-// One item (agent of one environment at one time slice) per thread.  step: CTA = G whole
-// environments.  rollout: CTA = G environments x TC concurrent time slices; (G, TC) is the pair
-// that fills the most threads of the CTA with TC <= 8, larger TC on ties.  DS_PLAN_G / DS_PLAN_TC
-// override the rollout plan (tuning experiments).
+// One row (agent of one environment at one time slice) per thread.  step: CTA = G whole
+// environments.  rollout: CTA = G environments x TC concurrent time slices.  The rollout kernel is
+// latency bound and compiled for DS_RO_MAXNREG = 96 registers: CTAs of ~160 threads (4 per SM)
+// measured best on B200 -- config 3: (G,TC) = (2,8) or (1,16) 1.30e10 agent-steps/s, 250-thread
+// CTAs 1.13e10; config 2: (4,8) 1.17e10; config 4: (1,4)/(1,5) 1.75e10 -- with chunks of about
+// 8 slices (shorter chunks pay the per-chunk barriers more often, longer ones add nothing).
+// Small batches trade environments per CTA for CTAs until the grid covers the SMs a few times.
+// DS_PLAN_G / DS_PLAN_TC override the rollout plan (tuning experiments).
 void plan_launch(ds_handle *h)
 {
     const int n = h->n, E = h->E;
@@ -160,31 +164,36 @@ void plan_launch(ds_handle *h)
     h->step_threads = ((h->step_G * n + 31) / 32) * 32;
     h->step_blocks = (int)(((long long)E + h->step_G - 1) / h->step_G);
     h->step_smem = cta_smem(h, h->step_G, 1);
-    int bestG = 1, bestTC = 1, best = 0;
-    const int tcmax = env_int("DS_PLAN_TCMAX", 8);
-    for (int TC = 1; TC <= tcmax; ++TC) {
-        const int G = clampG(cap / (n * TC));
-        const int items = G * n * TC;
-        if (items > cap && TC > 1) continue;
-        if (items >= best) { best = items; bestG = G; bestTC = TC; }
+    h->ro_NB = n <= 32 ? 1 : (n <= 128 ? 4 : 0);
+    h->ro_inline = (n <= 32) ? env_int("DS_PLAN_INLINE", 0) : 0;
+    const int lpr = env_int("DS_PLAN_LPR", 6);
+    auto list_cap = [&](int G, int TC) {                   // work list: room for lpr near pairs per row
+        int per_row = (n - 1 < lpr) ? (n - 1) : lpr;
+        per_row = (per_row < 1 || h->ro_inline) ? 1 : per_row;
+        int L = G * n * TC * per_row;
+        while (per_row > 1 && rollout_smem(h, G, TC, L) > h->smem_optin) L = G * n * TC * --per_row;
+        return L;
+    };
+    const int target = env_int("DS_PLAN_THREADS", 160) < cap ? env_int("DS_PLAN_THREADS", 160) : cap;
+    const int tcmax = env_int("DS_PLAN_TCMAX", 16);
+    int bestTC = target / n;
+    bestTC = bestTC < 1 ? 1 : (bestTC > 8 ? 8 : bestTC);
+    int bestG = clampG(target / (n * bestTC));
+    while (bestG > 1 && (E + bestG - 1) / bestG < 4 * h->sm_count) bestG /= 2;
+    if (bestG * n * bestTC * 2 <= target) {                // small batch: longer chunks instead
+        bestTC = target / (n * bestG);
+        bestTC = bestTC > tcmax ? tcmax : bestTC;
     }
     const int og = env_int("DS_PLAN_G", 0), otc = env_int("DS_PLAN_TC", 0);
     if (og > 0 && otc > 0 && og * n * otc <= cap) { bestG = clampG(og); bestTC = otc; }
     h->ro_G = bestG; h->ro_TC = bestTC;
     h->ro_threads = ((bestG * n * bestTC + 31) / 32) * 32;
     h->ro_blocks = (int)(((long long)E + bestG - 1) / bestG);
-    // work list: room for DS_PLAN_LPR (default 6) near pairs per row; rows that do not fit
-    // evaluate themselves (correct for any density, slower)
-    int per_row = (n - 1 < env_int("DS_PLAN_LPR", 6)) ? (n - 1) : env_int("DS_PLAN_LPR", 6);
-    per_row = per_row < 1 ? 1 : per_row;
-    h->ro_NB = n <= 32 ? 1 : (n <= 128 ? 4 : 0);
-    h->ro_inline = (n <= 32) ? env_int("DS_PLAN_INLINE", 0) : 0;
-    if (h->ro_inline) per_row = 1;                         // the list only serves the final reduction
-    for (;; --per_row) {
-        h->ro_L = bestG * n * bestTC * per_row;
-        h->ro_smem = rollout_smem(h, bestG, bestTC, h->ro_L);
-        if (h->ro_smem <= h->smem_optin || per_row == 1) break;
-    }
+    h->ro_L = list_cap(bestG, bestTC);
+    h->ro_smem = rollout_smem(h, bestG, bestTC, h->ro_L);
+    if (env_int("DS_PLAN_DEBUG", 0))
+        std::fprintf(stderr, "[dronestep] n=%d E=%d rollout plan: G=%d TC=%d threads=%d blocks=%d L=%d smem=%zu inline=%d\n",
+                     n, E, h->ro_G, h->ro_TC, h->ro_threads, h->ro_blocks, h->ro_L, h->ro_smem, h->ro_inline);
 }
 
 int check_params(const ds_params *p)
@@ -376,6 +385,7 @@ int ds_create(const ds_config *cfg, ds_handle **out)
     }
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->smem_sm = prop.sharedMemPerMultiprocessor;
     plan_launch(h);
     if (h->step_smem > (size_t)prop.sharedMemPerBlockOptin || h->ro_smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete h;

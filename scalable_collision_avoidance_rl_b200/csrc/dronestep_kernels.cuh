@@ -892,9 +892,6 @@ __device__ __forceinline__ unsigned pass1_block(const typename vec2_of<Real>::ty
     return __brev(~m) >> (32 - jn);
 }
 
-#ifndef DS_RO_MINB
-#define DS_RO_MINB 2      // CTAs of 256 threads per SM the rollout kernel is compiled for (register cap)
-#endif
 
 // Which slices of a chunk execute (drone_env.py:248-256): the episode ends at the first slice
 // whose agents are all at their goals (bit clear in ngbits) or whose t reaches max_steps - 1.
@@ -930,8 +927,16 @@ DS_HD int executed_slices(unsigned ngbits, int tt, int nsl, int max_steps, bool 
 //       posted to its frame / environment                                             | barrier
 //   (g) every row of an executed slice stores its outputs and adds to its running episode sums;
 //       one thread per environment advances t / alive                                 | barrier
+// Register cap of the 256-thread instantiations.  The kernel is latency bound, so resident warps
+// matter, but a cap that makes ptxas spill costs more than it gains: measured on B200 (config 3,
+// 160-thread CTAs) 96 registers / 4 CTAs per SM = 1.30e10 agent-steps/s, 104-112 / 3 CTAs = 1.16e10,
+// 80 with 50 B of spills / 5 CTAs = 1.09e10, 64-72 with 200-370 B of spills = 0.97-1.01e10.
+#ifndef DS_RO_MAXNREG
+#define DS_RO_MAXNREG 96
+#endif
+#define DS_RO_BOUNDS(NT) __launch_bounds__(NT) __maxnreg__((NT <= 256) ? DS_RO_MAXNREG : 64)
 template <typename Real, int K, int NT, int NB>
-__global__ void __launch_bounds__(NT, (NT <= 256) ? DS_RO_MINB : 1)
+__global__ void DS_RO_BOUNDS(NT)
 rollout_kernel(const RolloutArgs ra)
 {
     using V2 = typename vec2_of<Real>::type;

@@ -12,6 +12,6 @@ for lib in default "$@"; do
   for plan in "5 5" "2 8" "1 16"; do
     set -- $plan
     echo "== lib=$lib plan G=$1 TC=$2 hbm"
-    DS_PLAN_TCMAX=32 DS_PLAN_G=$1 DS_PLAN_TC=$2 timeout 300 python bench.py --workload hbm --no-cpu --no-e2e --steps 80 --warmup 20 --episode-steps 20 2>&1 | python -c "$summ"
+    DS_PLAN_G=$1 DS_PLAN_TC=$2 timeout 300 python bench.py --workload hbm --no-cpu --no-e2e --steps 80 --warmup 20 --episode-steps 20 2>&1 | python -c "$summ"
   done
 done

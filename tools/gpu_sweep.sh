@@ -18,6 +18,6 @@ for lib in default "$@"; do
   for plan in "${PL[@]}"; do
     set -- $plan
     echo "== lib=$lib plan G=$1 TC=$2 ${WL:-config3}"
-    DS_PLAN_TCMAX=32 DS_PLAN_G=$1 DS_PLAN_TC=$2 timeout 300 python bench.py --workload ${WL:-config3} --no-cpu --no-e2e --steps 4000 --warmup 600 2>&1 | python -c "$summ"
+    DS_PLAN_G=$1 DS_PLAN_TC=$2 timeout 300 python bench.py --workload ${WL:-config3} --no-cpu --no-e2e --steps 4000 --warmup 600 2>&1 | python -c "$summ"
   done
 done
