@@ -834,11 +834,15 @@ template <typename Real> struct RoSmem {
     V2 *cA;                  // [n] (d_safety, log d_safety)
     V2 *cB;                  // [n] (radius, delta)
     V2 *cF;                  // [n] end point
+    Real *cT;                // [n] pass-1 threshold
+    int *cC;                 // [n] Delta-disk count of the clipped pairs
     LogTabEntry *logtab;
-    V2 *act_, *pos_, *p0, *vfin, *res;   // act_ / pos_: two buffers of I rows (chunk parity)
+    V2 *act_, *pos_, *p0, *vfin, *res;   // act_: three, pos_: two buffers of I rows (chunk c mod 3 / mod 2)
+    V2 *accv;                // [I] running (sum r, sum true_r) of the row over the call
+    int *accc;               // [I] running collision count (rows with i == 0)
     unsigned *ent;
     int I_, G_;
-    int *cnt, *alive_, *tenv_, *lcount;  // alive_ / tenv_: per chunk parity
+    int *cnt, *alive_, *tenv_, *steps, *lcount;  // alive_ / tenv_: per chunk parity
     unsigned *ngbits;
     __device__ V2 *act(int b) const { return act_ + b * I_; }
     __device__ V2 *pos(int b) const { return pos_ + b * I_; }
@@ -848,9 +852,10 @@ template <typename Real> struct RoSmem {
     __host__ __device__ static size_t bytes(int n, int G, int TC, int L)
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
-        return (3 * (size_t)n + 4 * I + 2 * A + (size_t)L) * sizeof(V2) + kLogTabSize * sizeof(LogTabEntry) +
+        return (3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2) + kLogTabSize * sizeof(LogTabEntry) +
+               align16(n * sizeof(Real)) + align16(n * sizeof(int)) + align16(I * sizeof(int)) +
                align16((size_t)L * sizeof(unsigned)) + align16(F * sizeof(int)) +
-               align16((5 * (size_t)G + 1) * sizeof(int));
+               align16((6 * (size_t)G + 1) * sizeof(int));
     }
     __device__ RoSmem(unsigned char *base, int n, int G, int TC, int L)
     {
@@ -858,16 +863,32 @@ template <typename Real> struct RoSmem {
         unsigned char *p = base;
         I_ = (int)I; G_ = G;
         cA = reinterpret_cast<V2 *>(p); cB = cA + n; cF = cB + n;
-        act_ = cF + n; pos_ = act_ + 2 * I;
-        p0 = pos_ + 2 * I; vfin = p0 + A; res = vfin + A;
-        p += (3 * (size_t)n + 4 * I + 2 * A + (size_t)L) * sizeof(V2);
+        act_ = cF + n; pos_ = act_ + 3 * I;
+        p0 = pos_ + 2 * I; vfin = p0 + A; accv = vfin + A; res = accv + I;
+        p += (3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2);
         logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);
+        cT = reinterpret_cast<Real *>(p); p += align16(n * sizeof(Real));
+        cC = reinterpret_cast<int *>(p); p += align16(n * sizeof(int));
+        accc = reinterpret_cast<int *>(p); p += align16(I * sizeof(int));
         ent = reinterpret_cast<unsigned *>(p); p += align16((size_t)L * sizeof(unsigned));
         cnt = reinterpret_cast<int *>(p); p += align16(F * sizeof(int));
         alive_ = reinterpret_cast<int *>(p); tenv_ = alive_ + 2 * G;
-        ngbits = reinterpret_cast<unsigned *>(tenv_ + 2 * G); lcount = tenv_ + 3 * G;
+        ngbits = reinterpret_cast<unsigned *>(tenv_ + 2 * G); steps = tenv_ + 3 * G; lcount = tenv_ + 4 * G;
     }
 };
+
+// Ampere-style asynchronous global -> shared copy of one action (LDGSTS): the action stream of
+// chunk c + 2 is in flight while chunk c is evaluated, without holding it in registers.
+__device__ __forceinline__ void cp_async_action(double2 *dst, const double2 *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_action(float2 *dst, const float2 *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 // Pass 1 over one block of <= 32 agents of the row's frame: bit jj of the result = pair
 // (i, j0 + jj) is NOT provably clipped.  near <=> !(d2 >= thr2) <=> the sign bit of thr2 - d2 is
@@ -891,7 +912,6 @@ __device__ __forceinline__ unsigned pass1_block(const typename vec2_of<Real>::ty
     // m: NOT-near bits, agent jj at bit jn - 1 - jj
     return __brev(~m) >> (32 - jn);
 }
-
 
 // Which slices of a chunk execute (drone_env.py:248-256): the episode ends at the first slice
 // whose agents are all at their goals (bit clear in ngbits) or whose t reaches max_steps - 1.
@@ -949,6 +969,8 @@ rollout_kernel(const RolloutArgs ra)
         v.x = ((const Real *)a.c.d_safety)[idx]; v.y = ((const Real *)a.c.log_ds)[idx]; sm.cA[idx] = v;
         v.x = ((const Real *)a.c.radius)[idx]; v.y = ((const Real *)a.c.delta)[idx]; sm.cB[idx] = v;
         sm.cF[idx] = reinterpret_cast<const V2 *>(a.c.xF)[idx];
+        sm.cT[idx] = ((const Real *)a.c.thr2)[idx];
+        sm.cC[idx] = a.c.clipcnt[idx];
     }
     if (sizeof(Real) == 8)
         for (int idx = threadIdx.x; idx < kLogTabSize; idx += blockDim.x) sm.logtab[idx] = a.c.logtab[idx];
@@ -964,8 +986,6 @@ rollout_kernel(const RolloutArgs ra)
     const unsigned EN = (unsigned)E * n;
     const int fr = s * G + le;                        // frame slot of this thread
     const V2 *atab = reinterpret_cast<const V2 *>(ra.atable);
-    const Real thr2 = active ? ((const Real *)a.c.thr2)[i] : (Real)0;
-    const int clipcnt = active ? a.c.clipcnt[i] : 0;
     const bool agent_thread = tid < A && e < E;       // s == 0: owns agent ag across the call
     const bool env_thread = agent_thread && i == 0;   // owns environment le across the call
     // lanes of this warp that hold rows of the same frame; the first of them posts for the frame
@@ -981,17 +1001,17 @@ rollout_kernel(const RolloutArgs ra)
         sm.vfin[tid] = reinterpret_cast<const V2 *>(a.vel)[g];
         if (i == 0) { sm.alive(0)[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv(0)[le] = a.t[e]; }
     }
-    Real sum_r = 0, sum_tr = 0;                       // this row's share of the episode sums
-    int sum_c = 0, steps = 0;                         // i == 0 rows: collisions; env thread: steps
+    // running episode sums live in shared memory (registers are what limits residency)
+    if (active) { V2 z2; z2.x = 0; z2.y = 0; sm.accv[tid] = z2; sm.accc[tid] = 0; }
+    if (env_thread) sm.steps[le] = 0;
 
-    auto load_action = [&](unsigned at) -> V2 {
-        if (ra.actions) return reinterpret_cast<const V2 *>(ra.actions)[at];
-        return atab[ra.aidx[at]];
-    };
+    // action of this row at element index `at` -> act(b)[tid].  Explicit actions go global -> shared
+    // asynchronously (no registers); index mode keeps the prefetched u8 index in one register.
+    const bool direct = ra.actions != nullptr;
     // sequential integration of agent `tid` through nsl slices: pos(buf)[q] = start + dt u_0 .. u_q
-    auto integrate = [&](V2 p, int buf, int nsl) {
-        const V2 *ua = sm.act(buf) + tid;
-        V2 *pa = sm.pos(buf) + tid;
+    auto integrate = [&](V2 p, int abuf, int pbuf, int nsl) {
+        const V2 *ua = sm.act(abuf) + tid;
+        V2 *pa = sm.pos(pbuf) + tid;
         for (int q = 0; q < nsl; ++q) {
             const V2 uq = ua[q * A];
             p.x = add_rn(p.x, mul_rn(P.dt, uq.x));
@@ -1001,17 +1021,24 @@ rollout_kernel(const RolloutArgs ra)
     };
     unsigned at = (unsigned)s * EN + g;               // element index of this row at slice t0 + s
     unsigned fe = (unsigned)s * E + (unsigned)e;
-    // stage chunk 0; u_next always holds the prefetched action of the NEXT chunk's slice
-    V2 u_next{};
-    if (active && s < T) sm.act(0)[tid] = load_action(at);
-    if (active && TC + s < T) u_next = load_action(at + (unsigned)TC * EN);
+    // stage chunk 0 (synchronously) and chunk 1 (asynchronously / index prefetched)
+    unsigned ai_next = 0;
+    if (active && s < T)
+        sm.act(0)[tid] = direct ? reinterpret_cast<const V2 *>(ra.actions)[at] : atab[ra.aidx[at]];
+    if (active && TC + s < T) {
+        if (direct) cp_async_action(&sm.act(1)[tid], reinterpret_cast<const V2 *>(ra.actions) + at + (unsigned)TC * EN);
+        else sm.act(1)[tid] = atab[ra.aidx[at + (unsigned)TC * EN]];
+    }
+    cp_async_commit();
+    if (active && !direct && 2 * TC + s < T) ai_next = ra.aidx[at + 2u * (unsigned)TC * EN];
     if (tid == 0) *sm.lcount = 0;
     __syncthreads();
-    if (agent_thread && sm.alive(0)[le] != 0) integrate(sm.p0[tid], 0, (T < TC) ? T : TC);
+    if (agent_thread && sm.alive(0)[le] != 0) integrate(sm.p0[tid], 0, 0, (T < TC) ? T : TC);
     __syncthreads();
 
     // dense small-n frames: every row evaluates its own near pairs, two barriers per chunk
     const bool inl = (NB == 1) && ra.inline_rows != 0;
+    int ab = 0, ab1 = 1, ab2 = 2;                           // action buffers of chunk c, c + 1, c + 2
     for (int t0 = 0, buf = 0; t0 < T; t0 += TC, buf ^= 1) {
         const int nsl = (T - t0 < TC) ? (T - t0) : TC;      // slices in this chunk
         const bool in_chunk = active && s < nsl;
@@ -1027,6 +1054,7 @@ rollout_kernel(const RolloutArgs ra)
         if (env_thread) sm.ngbits[le] = 0;
         if (valid) {
             p = fpos[i];
+            const Real thr2 = sm.cT[i];
             if (i == 0) sm.cnt[fr] = 0;
             if (NB > 0) {
 #pragma unroll
@@ -1083,9 +1111,18 @@ rollout_kernel(const RolloutArgs ra)
                 }
             }
         }
-        // actions of the next chunk (integrated in (d)); prefetch the chunk after it
-        if (active && t0 + TC + s < T) sm.act(buf ^ 1)[tid] = u_next;
-        if (active && t0 + 2 * TC + s < T) u_next = load_action(at + 2u * (unsigned)TC * EN);
+        // actions of chunk c + 2 on their way to act(ab2); chunk c + 1's (issued one chunk ago) are
+        // complete after the wait and visible to the integration after the next barrier
+        if (active && t0 + 2 * TC + s < T) {
+            if (direct) {
+                cp_async_action(&sm.act(ab2)[tid], reinterpret_cast<const V2 *>(ra.actions) + at + 2u * (unsigned)TC * EN);
+            } else {
+                sm.act(ab2)[tid] = atab[ai_next];
+                if (t0 + 3 * TC + s < T) ai_next = ra.aidx[at + 3u * (unsigned)TC * EN];
+            }
+        }
+        cp_async_commit();
+        cp_async_wait_but_one();
         if (!inl) __syncthreads();
         // (d) pass 2: one near pair per thread per round
         if (!inl) {
@@ -1105,7 +1142,7 @@ rollout_kernel(const RolloutArgs ra)
         }
         if (!inl) {
             if (agent_thread && more && env_alive)
-                integrate(sm.pos(buf)[(TC - 1) * A + tid], buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
+                integrate(sm.pos(buf)[(TC - 1) * A + tid], ab1, buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
             __syncthreads();
         }
         // (e) rows
@@ -1115,7 +1152,8 @@ rollout_kernel(const RolloutArgs ra)
             AgentConst<Real> c;
             const V2 ca = sm.cA[i], cb = sm.cB[i], cf = sm.cF[i];
             c.xF = cf.x; c.yF = cf.y; c.ds = ca.x; c.log_ds = ca.y; c.radius = cb.x; c.delta = cb.y;
-            c.thr2 = thr2; c.clipcnt = clipcnt;
+            c.thr2 = 0; c.clipcnt = sm.cC[i];
+            p = fpos[i];
             if (inl)
                 eval_row_near32<Real, K>(o, n, i, p.x, p.y, c, near[0], fpos, sm.cB, P, sm.logtab);
             else if (listed)
@@ -1134,7 +1172,7 @@ rollout_kernel(const RolloutArgs ra)
         __syncthreads();
         // inline mode: the next chunk's actions are staged by now; integrate here
         if (inl && agent_thread && more && env_alive)
-            integrate(sm.pos(buf)[(TC - 1) * A + tid], buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
+            integrate(sm.pos(buf)[(TC - 1) * A + tid], ab1, buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
         // (g) stores
         int ne = 0;
         bool env_fin = false;
@@ -1143,7 +1181,7 @@ rollout_kernel(const RolloutArgs ra)
             if (s < ne) {
                 const int nc = sm.cnt[fr];
                 const bool fin = env_fin && s == ne - 1;
-                const V2 *fvel = sm.act(buf) + (tid - i);
+                const V2 *fvel = sm.act(ab) + (tid - i);
                 AgentConst<Real> c{};
                 { const V2 cb = sm.cB[i]; c.radius = cb.x; c.delta = cb.y; }
                 if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
@@ -1161,9 +1199,13 @@ rollout_kernel(const RolloutArgs ra)
                                        reinterpret_cast<Real *>(a.z), a.Ni, g, 2);
                     if (i == 0) { a.ncoll[e] = nc; a.fin[e] = fin ? 1 : 0; }
                 }
-                sum_r = add_rn(sum_r, o.r); sum_tr = add_rn(sum_tr, o.tr);
+                {
+                    V2 acc = sm.accv[tid];
+                    acc.x = add_rn(acc.x, o.r); acc.y = add_rn(acc.y, o.tr);
+                    sm.accv[tid] = acc;
+                }
                 if (i == 0) {
-                    sum_c += nc;
+                    sm.accc[tid] += nc;
                     if (ra.ncoll_tr) ra.ncoll_tr[fe] = nc;
                     if (ra.fin_tr) ra.fin_tr[fe] = fin ? 1 : 0;
                 }
@@ -1176,39 +1218,35 @@ rollout_kernel(const RolloutArgs ra)
         // one thread per agent: state after the last executed slice, when the call ends here
         if (agent_thread && env_alive && (env_fin || !more)) {
             sm.p0[tid] = sm.pos(buf)[(ne - 1) * A + tid];
-            sm.vfin[tid] = sm.act(buf)[(ne - 1) * A + tid];
+            sm.vfin[tid] = sm.act(ab)[(ne - 1) * A + tid];
         }
         // one thread per environment: t / alive of the next chunk (other parity)
         if (env_thread) {
-            steps += ne;
+            sm.steps[le] += ne;
             sm.tenv(buf ^ 1)[le] = sm.tenv(buf)[le] + ne;
             sm.alive(buf ^ 1)[le] = (env_alive && !env_fin) ? 1 : 0;
         }
         at += (unsigned)TC * EN; fe += (unsigned)TC * E;
+        { const int t3 = ab; ab = ab1; ab1 = ab2; ab2 = t3; }
         __syncthreads();
     }
     const int fbuf = ((T + TC - 1) / TC) & 1;                // parity the last chunk wrote
     // episode sums (train_problem.py:98-100): sum over the call of mean_i r, mean_i true_r, the
     // collision counts and the steps, reduced per environment in a fixed order
-    if (active) {
-        V2 v; v.x = sum_r; v.y = sum_tr;
-        sm.res[tid] = v;                                     // L >= I rows
-        sm.ent[tid] = (unsigned)sum_c;
-    }
-    __syncthreads();
     if (agent_thread) {
         reinterpret_cast<V2 *>(a.pos)[g] = sm.p0[tid];
         reinterpret_cast<V2 *>(a.vel)[g] = sm.vfin[tid];
     }
     if (env_thread) {
         a.t[e] = sm.tenv(fbuf)[le];
+        const int steps = sm.steps[le];
         if (steps > 0) {
             if (sm.alive(fbuf)[le] == 0) ra.done[e] = 1;
             double sr = 0, st = 0, sc = 0;
             for (int q = 0; q < TC; ++q) {
-                const V2 *rv = sm.res + q * A + le * n;
+                const V2 *rv = sm.accv + q * A + le * n;
                 for (int j = 0; j < n; ++j) { sr += (double)rv[j].x; st += (double)rv[j].y; }
-                sc += (double)(int)sm.ent[q * A + le * n];
+                sc += (double)sm.accc[q * A + le * n];
             }
             double *ag4 = ra.agg + (size_t)e * 4;
             ag4[0] += sr / n; ag4[1] += st / n; ag4[2] += sc; ag4[3] += (double)steps;
