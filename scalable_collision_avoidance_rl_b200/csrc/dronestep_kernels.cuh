@@ -1152,7 +1152,7 @@ rollout_kernel(const RolloutArgs ra)
             AgentConst<Real> c;
             const V2 ca = sm.cA[i], cb = sm.cB[i], cf = sm.cF[i];
             c.xF = cf.x; c.yF = cf.y; c.ds = ca.x; c.log_ds = ca.y; c.radius = cb.x; c.delta = cb.y;
-            c.thr2 = 0; c.clipcnt = sm.cC[i];
+            c.thr2 = sm.cT[i]; c.clipcnt = sm.cC[i];
             p = fpos[i];
             if (inl)
                 eval_row_near32<Real, K>(o, n, i, p.x, p.y, c, near[0], fpos, sm.cB, P, sm.logtab);

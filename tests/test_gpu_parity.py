@@ -303,6 +303,93 @@ def test_full_size_properties():
     assert int(env.n_collisions.sum()) == int(ref.ncoll.sum())
 
 
+FULL = [  # BASELINE.json configs 2-5 at their full batch sizes; T bounded by the oracle's time
+    ("config2", 5, 4096, [5, 5], 1.0, 200),
+    ("config3", 10, 4096, [5, 5], 1.0, 200),
+    ("config4", 32, 8192, [32, 32], 2.5, 40),
+    ("config5", 128, 1024, [64, 64], 1.0, 24),
+]
+
+
+@pytest.mark.parametrize("name,n,E,grid,delta,T", FULL, ids=[c[0] for c in FULL])
+def test_rollout_full_size_vs_oracle(name, n, E, grid, delta, T):
+    """The benchmarked launch itself -- one fused rollout of the whole BASELINE batch, every output
+    recorded -- against the C oracle stepping the same environments with the same action stream."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    rng = np.random.default_rng(42)
+    env = BatchedDrones(E, n, grid, "O", 2, np.ones(n) * delta, True, seed=3, warn=False)
+    start = env.pos.cpu().numpy().copy()
+    tab = formation.unit_action_table(16)
+    idx = rng.integers(0, 16, (T, E, n)).astype(np.uint8)
+    act = tab[idx]
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, 2, True,
+                             c_oracle.default_params(env.collision_weight), nthreads=16)
+    orc.set_state(start)
+    ref = orc.rollout(act)
+    rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
+    out = env.rollout(actions=torch.as_tensor(act, device=env.device), record=rec)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["finished"].cpu().numpy(), ref["finished"])
+    live = ref["finished"] != 2
+    assert_close(out["reward"].cpu().numpy()[live], ref["r"][live], FP64_TOL, "reward")
+    assert_close(out["true_reward"].cpu().numpy()[live], ref["true_r"][live], FP64_TOL, "true reward")
+    assert np.array_equal(out["ncoll"].cpu().numpy()[live], ref["ncoll"][live]), "collision counts"
+    assert_close(out["agg"].cpu().numpy(), ref["agg"], 1e-8, "episode aggregates")
+    assert_close(env.pos.cpu().numpy(), ref["pos"], 0.0, "final positions (bit-exact)")
+    assert np.array_equal(env.internal_t.cpu().numpy(), ref["t"])
+    # last recorded observation == the oracle's (tie aware) == live buffers == a fresh observe()
+    z_last, Ni_last = out["z"][T - 1].clone(), out["Ni"][T - 1].clone()
+    compare_obs(z_last.cpu().numpy(), Ni_last.cpu().numpy(), ref["z"], ref["Ni"], orc.tie, FP64_TOL, name)
+    assert torch.equal(z_last, env.z_states) and torch.equal(Ni_last, env.Ni)
+    env.observe()
+    torch.cuda.synchronize()
+    assert torch.equal(z_last, env.z_states) and torch.equal(Ni_last, env.Ni)
+    # size-independent invariants of the recorded trajectory
+    assert torch.equal(out["vel"], torch.as_tensor(act, device=env.device))         # v <- u (:238)
+    Ni = out["Ni"].cpu().numpy()
+    assert (Ni[..., 0] == np.arange(n)).all() and (Ni >= -1).all() and (Ni < n).all()
+    assert (out["ncoll"].cpu().numpy() % 2 == 0).all()
+
+
+@pytest.mark.parametrize("n,E,grid,delta,box,k,hetero", [
+    (10, 300, [5, 5], 1.0, 1.0, 2, False),     # every pair near: the work list overflows, rows evaluate themselves
+    (24, 64, [8, 8], 1.5, 2.0, 3, True),       # dense, heterogeneous Delta, k = 3
+    (200, 6, [128, 128], 1.0, 30.0, 2, False), # 128 < n <= 256: near masks in local memory
+    (300, 4, [128, 128], 1.0, 30.0, 2, False), # n > 256: 1024-thread CTAs
+])
+def test_rollout_dense_and_large(n, E, grid, delta, box, k, hetero):
+    """Rollout paths the BASELINE configs do not reach: list overflow, dense frames with many
+    collisions and ties, large n.  Checked against the oracle's episode loop."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    T = 12
+    rng = np.random.default_rng(7 * n)
+    deltas = rng.uniform(0.3, delta, n) if hetero else np.ones(n) * delta
+    env = BatchedDrones(E, n, grid, "O", k, deltas, False, seed=2, warn=False)
+    pos = rng.uniform(0, box, (E, n, 2))
+    state = np.concatenate([pos, np.zeros((E, n, 2)), np.full((E, n, 1), 0.1)], 2)
+    env.set_state(state, np.zeros(E, np.int32))
+    act = rng.uniform(-1, 1, (T, E, n, 2))
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, k, False,
+                             c_oracle.default_params(env.collision_weight), nthreads=8)
+    orc.set_state(pos)
+    ref = orc.rollout(act)
+    out = env.rollout(actions=torch.as_tensor(act, device=env.device),
+                      record=("reward", "true_reward", "obs", "ncoll", "finished"))
+    torch.cuda.synchronize()
+    assert ref["ncoll"].sum() > 0 or box > 20
+    assert np.array_equal(out["finished"].cpu().numpy(), ref["finished"])
+    assert_close(out["reward"].cpu().numpy(), ref["r"], FP64_TOL, "reward")
+    assert_close(out["true_reward"].cpu().numpy(), ref["true_r"], FP64_TOL, "true reward")
+    assert np.array_equal(out["ncoll"].cpu().numpy(), ref["ncoll"])
+    assert_close(env.pos.cpu().numpy(), ref["pos"], 0.0, "final positions")
+    # the fused rollout's observations == the oracle's (tie aware) == the step kernel's on the final state
+    z_last, Ni_last = out["z"][T - 1].clone(), out["Ni"][T - 1].clone()
+    compare_obs(z_last.cpu().numpy(), Ni_last.cpu().numpy(), ref["z"], ref["Ni"], orc.tie, FP64_TOL, "final obs")
+    env.observe()
+    torch.cuda.synchronize()
+    assert torch.equal(z_last, env.z_states) and torch.equal(Ni_last, env.Ni)
+
+
 def test_error_behaviour():
     from scalable_collision_avoidance_rl_b200 import BatchedDrones, DroneStepError
     with pytest.raises(DroneStepError):
