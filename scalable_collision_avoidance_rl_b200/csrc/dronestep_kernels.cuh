@@ -21,7 +21,10 @@
 //   pass 1  squared distance against a per-agent threshold: every pair that is
 //           provably clipped to d_safety (drone_env.py:318 min(.., d_safety[i]))
 //           contributes log(1) = 0, no collision, and a Delta-disk count that is a
-//           per-agent constant -- 6 instructions, no sqrt;
+//           per-agent constant -- no sqrt.  The step kernel does it in fp64 (7
+//           instructions per pair); the rollout kernel on the packed-f32 pipe
+//           (FADD2 / FMUL2 / FFMA2, two pairs per instruction) against a threshold
+//           with a margin: the mask only has to be a superset of the live pairs;
 //   pass 2  only the NEAR pairs take the exact path: sqrt, clip, zero rule,
 //           division, log, collision test, k-nearest insert.
 // In the rollout kernel the near pairs of all rows of the CTA are compacted into a
@@ -834,8 +837,11 @@ template <typename Real> struct RoSmem {
     V2 *cA;                  // [n] (d_safety, log d_safety)
     V2 *cB;                  // [n] (radius, delta)
     V2 *cF;                  // [n] end point
-    Real *cT;                // [n] pass-1 threshold
+    float *cTf;              // [n] pass-1 threshold of the packed-f32 filter (squared, with margin)
     int *cC;                 // [n] Delta-disk count of the clipped pairs
+    Real *cT;                // [n] exact pass-1 threshold (rows that evaluate themselves)
+    float4 *pf_;             // two buffers of F * hp: (x_2q, x_2q+1, y_2q, y_2q+1) of each frame, f32
+    int hp_, F_;
     LogTabEntry *logtab;
     V2 *act_, *pos_, *p0, *vfin, *res;   // act_: three, pos_: two buffers of I rows (chunk c mod 3 / mod 2)
     V2 *accv;                // [I] running (sum r, sum true_r) of the row over the call
@@ -846,6 +852,7 @@ template <typename Real> struct RoSmem {
     unsigned *ngbits;
     __device__ V2 *act(int b) const { return act_ + b * I_; }
     __device__ V2 *pos(int b) const { return pos_ + b * I_; }
+    __device__ float4 *pf(int b) const { return pf_ + b * F_ * hp_; }
     __device__ int *alive(int b) const { return alive_ + b * G_; }
     __device__ int *tenv(int b) const { return tenv_ + b * G_; }
     __host__ __device__ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -853,7 +860,8 @@ template <typename Real> struct RoSmem {
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
         return (3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2) + kLogTabSize * sizeof(LogTabEntry) +
-               align16(n * sizeof(Real)) + align16(n * sizeof(int)) + align16(I * sizeof(int)) +
+               align16(n * sizeof(Real)) + align16(n * sizeof(int)) + align16(n * sizeof(float)) +
+               2 * F * ((n + 1) / 2) * sizeof(float4) + align16(I * sizeof(int)) +
                align16((size_t)L * sizeof(unsigned)) + align16(F * sizeof(int)) +
                align16((6 * (size_t)G + 1) * sizeof(int));
     }
@@ -867,8 +875,11 @@ template <typename Real> struct RoSmem {
         p0 = pos_ + 2 * I; vfin = p0 + A; accv = vfin + A; res = accv + I;
         p += (3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2);
         logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);
+        hp_ = (n + 1) / 2; F_ = (int)F;
+        pf_ = reinterpret_cast<float4 *>(p); p += 2 * F * hp_ * sizeof(float4);
         cT = reinterpret_cast<Real *>(p); p += align16(n * sizeof(Real));
         cC = reinterpret_cast<int *>(p); p += align16(n * sizeof(int));
+        cTf = reinterpret_cast<float *>(p); p += align16(n * sizeof(float));
         accc = reinterpret_cast<int *>(p); p += align16(I * sizeof(int));
         ent = reinterpret_cast<unsigned *>(p); p += align16((size_t)L * sizeof(unsigned));
         cnt = reinterpret_cast<int *>(p); p += align16(F * sizeof(int));
@@ -911,6 +922,34 @@ __device__ __forceinline__ unsigned pass1_block(const typename vec2_of<Real>::ty
     }
     // m: NOT-near bits, agent jj at bit jn - 1 - jj
     return __brev(~m) >> (32 - jn);
+}
+
+// Pass 1 of the rollout kernel on Blackwell's packed-f32 pipe (FADD2 / FMUL2 / FFMA2: two pairs per
+// instruction, 4 instructions per pair instead of 7 and nothing on the FP64 pipe).  The near mask
+// only has to be a SUPERSET of the pairs that are not clipped -- the exact fp64 path handles a
+// clipped pair correctly -- so an f32 distance against a threshold with a margin far above the
+// f32 rounding of coordinates below 1024 is enough; agents with non-finite or larger coordinates
+// are stored as NaN, which makes every pair they are in "near" (sign bit of thr - d2 clear).
+// fp: float4 per two agents (x0, x1, y0, y1); nx, ny: MINUS the row's own f32 position.
+__device__ __forceinline__ unsigned pass1_block_f32x2(const float4 *__restrict__ fp, int jn, float nx, float ny,
+                                                      float thr2f)
+{
+    const float2 NX = make_float2(nx, nx), NY = make_float2(ny, ny);
+    const float2 TH = make_float2(thr2f, thr2f), M1 = make_float2(-1.0f, -1.0f);
+    const int np = (jn + 1) >> 1;
+    unsigned m = 0;
+#pragma unroll 4
+    for (int q = 0; q < np; ++q) {
+        const float4 pq = fp[q];
+        const float2 a = __fadd2_rn(make_float2(pq.x, pq.y), NX);
+        const float2 b = __fadd2_rn(make_float2(pq.z, pq.w), NY);
+        const float2 t = __ffma2_rn(__ffma2_rn(b, b, __fmul2_rn(a, a)), M1, TH);   // thr2 - d2
+        m = __funnelshift_l(__float_as_uint(t.x), m, 1);
+        m = __funnelshift_l(__float_as_uint(t.y), m, 1);
+    }
+    // m: NOT-near bits of 2 np agents, agent jj at bit 2 np - 1 - jj (a pad agent sits at 1e30: not near)
+    m = __brev(~m) >> (32 - 2 * np);
+    return (jn < 32) ? (m & ((1u << jn) - 1u)) : m;
 }
 
 // Which slices of a chunk execute (drone_env.py:248-256): the episode ends at the first slice
@@ -971,6 +1010,10 @@ rollout_kernel(const RolloutArgs ra)
         sm.cF[idx] = reinterpret_cast<const V2 *>(a.c.xF)[idx];
         sm.cT[idx] = ((const Real *)a.c.thr2)[idx];
         sm.cC[idx] = a.c.clipcnt[idx];
+        {   // (sqrt(thr2) + 2e-3)^2 rounded up: margin >> f32 rounding of |coordinates| < 1024
+            const double th = sqrt((double)sm.cT[idx]) + 2e-3;
+            sm.cTf[idx] = __double2float_ru(th * th);
+        }
     }
     if (sizeof(Real) == 8)
         for (int idx = threadIdx.x; idx < kLogTabSize; idx += blockDim.x) sm.logtab[idx] = a.c.logtab[idx];
@@ -1012,11 +1055,19 @@ rollout_kernel(const RolloutArgs ra)
     auto integrate = [&](V2 p, int abuf, int pbuf, int nsl) {
         const V2 *ua = sm.act(abuf) + tid;
         V2 *pa = sm.pos(pbuf) + tid;
+        // f32 copy for pass 1: component (i & 1) of x / y in float4 (i >> 1) of frame q * G + le
+        float *pfa = reinterpret_cast<float *>(sm.pf(pbuf) + le * sm.hp_ + (i >> 1)) + (i & 1);
+        const int fstride = G * sm.hp_ * 4;                  // floats per slice
+        const bool pad = (i == n - 1) && (n & 1);            // odd n: the missing partner never is near
         for (int q = 0; q < nsl; ++q) {
             const V2 uq = ua[q * A];
             p.x = add_rn(p.x, mul_rn(P.dt, uq.x));
             p.y = add_rn(p.y, mul_rn(P.dt, uq.y));
             pa[q * A] = p;
+            const bool ok = fabs(p.x) < (Real)1024 && fabs(p.y) < (Real)1024;   // false for NaN / inf too
+            pfa[q * fstride] = ok ? (float)p.x : __int_as_float(0x7fc00000);
+            pfa[q * fstride + 2] = ok ? (float)p.y : __int_as_float(0x7fc00000);
+            if (pad) { pfa[q * fstride + 1] = 1e30f; pfa[q * fstride + 3] = 1e30f; }
         }
     };
     unsigned at = (unsigned)s * EN + g;               // element index of this row at slice t0 + s
@@ -1054,15 +1105,18 @@ rollout_kernel(const RolloutArgs ra)
         if (env_thread) sm.ngbits[le] = 0;
         if (valid) {
             p = fpos[i];
-            const Real thr2 = sm.cT[i];
             if (i == 0) sm.cnt[fr] = 0;
+            const float4 *ffr = sm.pf(buf) + fr * sm.hp_;    // packed f32 positions of this row's frame
+            const float thr2f = sm.cTf[i];
+            const float nx = -reinterpret_cast<const float *>(ffr + (i >> 1))[i & 1];
+            const float ny = -reinterpret_cast<const float *>(ffr + (i >> 1))[2 + (i & 1)];
             if (NB > 0) {
 #pragma unroll
                 for (int bk = 0; bk < NBR; ++bk) {
                     const int j0 = bk * 32;
                     unsigned m = 0;
                     if (j0 < n) {
-                        m = pass1_block<Real>(fpos + j0, (n - j0 < 32) ? (n - j0) : 32, p.x, p.y, thr2);
+                        m = pass1_block_f32x2(ffr + j0 / 2, (n - j0 < 32) ? (n - j0) : 32, nx, ny, thr2f);
                         if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
                     }
                     near[bk] = m;
@@ -1070,7 +1124,7 @@ rollout_kernel(const RolloutArgs ra)
                 }
             } else {
                 for (int j0 = 0, bk = 0; j0 < n; j0 += 32, ++bk) {
-                    unsigned m = pass1_block<Real>(fpos + j0, (n - j0 < 32) ? (n - j0) : 32, p.x, p.y, thr2);
+                    unsigned m = pass1_block_f32x2(ffr + j0 / 2, (n - j0 < 32) ? (n - j0) : 32, nx, ny, thr2f);
                     if ((unsigned)(i - j0) < 32u) m &= ~(1u << (i - j0));
                     near[bk] = m;
                     ncnt += __popc(m);
