@@ -54,6 +54,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout launch from the committed
+# `ncu --set full` captures (profiles/r01/*_summary.md), keyed by (workload, dtype): bytes per launch.
+NCU_TRAFFIC = {
+    ("config3", "f64"): 133.4e6 + 836.8e6,     # profiles/r01/final_prof_config3_summary.md
+    ("config5", "f64"): 424.1e6 + 2788.5e6,    # profiles/r01/e_prof_config5_summary.md
+}
+
+
 def bytes_per_agent_step(rb, n, k=K_CLOSEST, cols=2, mode="rollout"):
     """Algorithmic HBM bytes per agent-step.
     rollout: read action 2*rb; write pos 2*rb, vel 2*rb, r rb, true_r rb, z (k+1)*cols*rb,
@@ -368,9 +376,13 @@ def run_ours(args, wl):
                    "l2": f"inputs larger than L2: {alg_bytes_launch / 1e6:.0f} MB streamed per launch",
                    "log_mode": args.log_mode},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak,
+                     "traffic": NCU_TRAFFIC.get((args.workload, args.dtype)) if T == EPISODE else None,
+                     "traffic_unit": "DRAM bytes per launch (ncu capture, profiles/r01)",
+                     "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src,
                      "kernel": "ds::rollout_kernel", "bytes_per_agent_step": bpas,
-                     "avg_launch_ms": avg_ms, "launches_timed": len(kms)},
+                     "avg_launch_ms": avg_ms, "launches_timed": len(kms),
+                     "note": "the kernel is issue/latency bound, not HBM bound (DESIGN.md section 5)"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches[0], "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
