@@ -147,6 +147,26 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io,
  * (train_problem.py:118-121).  out is caller-owned device memory. */
 int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, void *cuda_stream);
 
+/* Monte-Carlo returns and Delta-neighbourhood advantage sums of a recorded rollout -- what the
+ * reference's learners compute on the host from their ExperienceBuffers (SAC_agents.py:304-310 /
+ * 108-113: G_i(t) = G_i(t+1) * discount + r_i(t) backwards from the episode's last step;
+ * SAC_agents.py:333-345: A_i(t) = sum over j in N_i(t) of (G_j(t) - V_i(t)), in list order).
+ * Inputs are the trajectory buffers ds_rollout writes (device pointers); an environment's episode
+ * ends at its last executed step (finished code != 2); not-executed steps get zeros. */
+typedef struct ds_returns_io {
+    int32_t T;
+    int32_t _pad;
+    double discount;             /* SAC_agents.py:129 (0.99) */
+    const void *reward_tr;       /* Real [T][E][n] */
+    const int32_t *Ni_tr;        /* i32  [T][E][n][k+1], -1 padded */
+    const uint8_t *finished_tr;  /* u8   [T][E], codes of ds_rollout_io.finished_tr */
+    const void *baseline;        /* Real [T][E][n]: V_i(z_i(t)) of the critic, or NULL for 0 */
+    void *returns;               /* out Real [T][E][n] */
+    void *advantage;             /* out Real [T][E][n] */
+    uint8_t *count;              /* out u8 [T][E][n]: |N_i(t)| (may be NULL) */
+} ds_returns_io;
+int ds_returns(ds_handle *h, const ds_returns_io *io, void *cuda_stream);
+
 /* Host-buffer variants: state[E][n][5] float64 in the reference's row layout
  * [x, y, vx, vy, l] (drone_env.py:173,189-190). */
 int ds_set_state(ds_handle *h, const double *state_host, const int32_t *t_host,

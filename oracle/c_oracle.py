@@ -60,6 +60,7 @@ def lib():
         _lib = ctypes.CDLL(path)
         _lib.oracle_step_batch.restype = ctypes.c_int
         _lib.oracle_rollout_batch.restype = ctypes.c_int
+        _lib.oracle_returns_batch.restype = ctypes.c_int
     return _lib
 
 
@@ -157,3 +158,22 @@ class OracleEnv:
         return dict(agg=agg, r=r_tr, true_r=t_tr, ncoll=c_tr, finished=f_tr, done=done,
                     pos=self.pos.copy(), vel=self.vel.copy(), z=self.z.copy(), Ni=self.Ni.copy(),
                     t=self.t.copy())
+
+
+def returns(reward_tr, Ni_tr, finished_tr, discount, baseline=None):
+    """Monte-Carlo returns and Delta-neighbourhood advantage sums of a recorded rollout
+    (reference SAC_agents.py:304-310,333-345): reward_tr [T,E,n], Ni_tr [T,E,n,k+1] (-1 padded),
+    finished_tr [T,E] (0/1/2).  Returns (G [T,E,n], adv [T,E,n], cnt [T,E,n] int32)."""
+    r = np.ascontiguousarray(np.asarray(reward_tr, np.float64))
+    Ni = np.ascontiguousarray(np.asarray(Ni_tr, np.int32))
+    fin = np.ascontiguousarray(np.asarray(finished_tr, np.uint8))
+    T, E, n = r.shape
+    k = Ni.shape[-1] - 1
+    assert Ni.shape == (T, E, n, k + 1) and fin.shape == (T, E)
+    base = None if baseline is None else np.ascontiguousarray(np.asarray(baseline, np.float64))
+    G = np.zeros((T, E, n)); adv = np.zeros((T, E, n)); cnt = np.zeros((T, E, n), np.int32)
+    rc = lib().oracle_returns_batch(E, n, k, T, ctypes.c_double(discount), _p(r), _p(Ni), _p(fin), _p(base),
+                                    _p(G), _p(adv), _p(cnt))
+    if rc != 0:
+        raise ValueError(f"oracle_returns_batch failed rc={rc}")
+    return G, adv, cnt

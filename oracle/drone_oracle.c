@@ -351,4 +351,54 @@ int oracle_rollout_batch(int E, int n, int k, int simplify, int T, const oracle_
     return 0;
 }
 
+/* ---------------------------------------------------------------- returns / advantages
+ * what the learners do with the rollout's reward and Ni trajectories.
+ *   returns     G_i(t) = G_i(t+1) * discount + r_i(t), G_i(last) = r_i(last)
+ *               (SAC_agents.py:304-310 in SA2CAgents.train_NN; :108-113 in TrainedAgent.benchmark_cirtic)
+ *   advantages  A_i(t) = sum over j in N_i(t), in list order, of (G_j(t) - V_i(t)), from 0
+ *               (SAC_agents.py:333-345; V = the critic's baseline, 0 when none is given)
+ * Batched over E environments with the rollout's finished codes (0 running, 1 finished at this
+ * step, 2 not executed): the episode of environment e ends at its first code-1 step, else at the
+ * last executed step; steps that were not executed get zeros. */
+int oracle_returns_batch(int E, int n, int k, int T, double discount, const double *r_tr, const int32_t *Ni_tr,
+                         const uint8_t *fin_tr, const double *baseline, double *G, double *adv, int32_t *cnt)
+{
+    if (E < 1 || n < 1 || k < 0 || T < 0) return -1;
+    const size_t EN = (size_t)E * n;
+    for (int e = 0; e < E; ++e) {
+        int last = -1;
+        for (int t = 0; t < T; ++t) {
+            const uint8_t f = fin_tr[(size_t)t * E + e];
+            if (f == 2) break;
+            last = t;
+            if (f == 1) break;
+        }
+        for (int t = T - 1; t > last; --t)
+            for (int i = 0; i < n; ++i) {
+                const size_t a = (size_t)t * EN + (size_t)e * n + i;
+                G[a] = 0.0; adv[a] = 0.0; cnt[a] = 0;
+            }
+        for (int t = last; t >= 0; --t)
+            for (int i = 0; i < n; ++i) {
+                const size_t a = (size_t)t * EN + (size_t)e * n + i;
+                G[a] = (t == last) ? r_tr[a] : G[a + EN] * discount + r_tr[a];      /* :306-309 */
+            }
+        for (int t = 0; t <= last; ++t)
+            for (int i = 0; i < n; ++i) {
+                const size_t a = (size_t)t * EN + (size_t)e * n + i;
+                const double v = baseline ? baseline[a] : 0.0;
+                double sum = 0.0;                                                   /* :339 */
+                int c = 0;
+                for (int m = 0; m <= k; ++m) {
+                    const int32_t j = Ni_tr[a * (size_t)(k + 1) + m];
+                    if (j < 0) continue;
+                    sum += G[(size_t)t * EN + (size_t)e * n + j] - v;                /* :344-345 */
+                    ++c;
+                }
+                adv[a] = sum; cnt[a] = c;
+            }
+    }
+    return 0;
+}
+
 int oracle_abi_version(void) { return 1; }

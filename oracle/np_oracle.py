@@ -105,3 +105,33 @@ def step(pos, vel, t, act, radius, xF, d_safety, deltas, k, simplify, collision_
     out["finished"] = ((err <= GOAL_TOL).all(1) | (t >= max_time_steps - 1)).astype(np.uint8)  # :251
     t += 1                   # :256
     return out
+
+
+def returns(reward_tr, Ni_tr, finished_tr, discount, baseline=None):
+    """NumPy restatement of the return scan and the Delta-neighbourhood advantage gather
+    (reference SAC_agents.py:304-310,333-345); same contract as ``c_oracle.returns``."""
+    r = np.asarray(reward_tr, np.float64)
+    Ni = np.asarray(Ni_tr); fin = np.asarray(finished_tr)
+    T, E, n = r.shape
+    k = Ni.shape[-1] - 1
+    executed = np.cumsum(fin == 2, axis=0) == 0                       # [T,E]: slice was stepped
+    prev_fin = np.concatenate([np.zeros((1, E), bool), np.cumsum(fin == 1, axis=0)[:-1] > 0])
+    executed &= ~prev_fin
+    G = np.zeros((T, E, n))
+    nxt = np.zeros((E, n))
+    started = np.zeros(E, bool)
+    for t in range(T - 1, -1, -1):                                    # SAC_agents.py:306-309
+        ex = executed[t]
+        g = np.where(started[:, None], nxt * discount + r[t], r[t])
+        G[t] = np.where(ex[:, None], g, 0.0)
+        nxt = np.where(ex[:, None], g, nxt)
+        started |= ex
+    base = np.zeros((T, E, n)) if baseline is None else np.asarray(baseline, np.float64)
+    adv = np.zeros((T, E, n)); cnt = np.zeros((T, E, n), np.int32)
+    for m in range(k + 1):                                            # list order (:344-345)
+        j = Ni[..., m]
+        valid = (j >= 0) & executed[..., None]
+        gj = np.take_along_axis(G, np.where(j >= 0, j, 0), axis=2)
+        adv = np.where(valid, adv + (gj - base), adv)
+        cnt += valid
+    return G, adv, cnt

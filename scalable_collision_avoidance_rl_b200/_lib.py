@@ -20,7 +20,7 @@ DS_MAX_AGENTS, DS_MAX_K = 1024, 16
 EXPORTED_SYMBOLS = (
     "ds_abi_version", "ds_last_error", "ds_device_count", "ds_create", "ds_destroy",
     "ds_default_params", "ds_step", "ds_observe", "ds_rollout", "ds_reduce_aggregates",
-    "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_rollout_host",
+    "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_rollout_host", "ds_returns",
 )
 
 
@@ -53,6 +53,12 @@ class ds_rollout_io(ctypes.Structure):
                 ("vel_tr", c_void_p), ("reward_tr", c_void_p), ("true_reward_tr", c_void_p),
                 ("z_tr", c_void_p), ("Ni_tr", c_void_p), ("ncoll_tr", c_void_p),
                 ("finished_tr", c_void_p), ("agg", c_void_p), ("done", c_void_p)]
+
+
+class ds_returns_io(ctypes.Structure):
+    _fields_ = [("T", c_int32), ("_pad", c_int32), ("discount", c_double), ("reward_tr", c_void_p),
+                ("Ni_tr", c_void_p), ("finished_tr", c_void_p), ("baseline", c_void_p),
+                ("returns", c_void_p), ("advantage", c_void_p), ("count", c_void_p)]
 
 
 class ds_host_step_out(ctypes.Structure):

@@ -313,6 +313,40 @@ class BatchedDrones:
                                             ctypes.byref(hr), self._stream()), "ds_rollout_host")
         return out
 
+    def returns(self, reward, Ni, finished, discount=0.99, baseline=None, out=None):
+        """Monte-Carlo returns G_i(t) and Delta-neighbourhood advantage sums
+        sum_{j in N_i(t)} (G_j(t) - V_i(t)) of a recorded rollout, on the device (ds_returns;
+        reference SAC_agents.py:304-310, 333-345).  reward [T,E,n], Ni [T,E,n,k+1] and
+        finished [T,E] are the trajectory tensors rollout() records ('reward', 'Ni', 'finished');
+        baseline [T,E,n] is the critic's V (None = 0).  Returns dict(returns, advantage, count)."""
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        T = reward.shape[0]
+        assert tuple(reward.shape) == (T, E, n) and reward.dtype == self.dtype and reward.is_cuda
+        assert tuple(Ni.shape) == (T, E, n, k + 1) and Ni.dtype == torch.int32
+        assert tuple(finished.shape) == (T, E) and finished.dtype == torch.uint8
+        reward, Ni, finished = reward.contiguous(), Ni.contiguous(), finished.contiguous()
+        if baseline is not None:
+            baseline = baseline.to(self.dtype).contiguous()
+            assert tuple(baseline.shape) == (T, E, n)
+        out = {} if out is None else out
+
+        def buf(name, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != (T, E, n) or t.dtype != dtype:
+                t = torch.empty((T, E, n), dtype=dtype, device=self.device)
+                out[name] = t
+            return t
+
+        io = _lib.ds_returns_io()
+        io.T, io.discount = T, float(discount)
+        io.reward_tr, io.Ni_tr, io.finished_tr = reward.data_ptr(), Ni.data_ptr(), finished.data_ptr()
+        io.baseline = None if baseline is None else baseline.data_ptr()
+        io.returns = buf("returns", self.dtype).data_ptr()
+        io.advantage = buf("advantage", self.dtype).data_ptr()
+        io.count = buf("count", torch.uint8).data_ptr()
+        _lib.check(self.lib.ds_returns(self._h, ctypes.byref(io), self._stream()), "ds_returns")
+        return out
+
     def episode_aggregates(self):
         """Device-side sum over this rank's environments of the per-env episode accumulators
         -> float64 [5] = (sum_t mean_i r, sum_t mean_i true_r, sum_t collisions, steps, #envs):

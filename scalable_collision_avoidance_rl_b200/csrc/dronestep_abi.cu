@@ -480,6 +480,40 @@ int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, v
     return DS_OK;
 }
 
+int ds_returns(ds_handle *h, const ds_returns_io *io, void *cuda_stream)
+{
+    if (!h || !io) return fail(DS_ERR_ARG, "ds_returns: NULL argument");
+    if (io->T < 0) return fail(DS_ERR_ARG, "ds_returns: T < 0");
+    if (!io->reward_tr || !io->Ni_tr || !io->finished_tr || !io->returns || !io->advantage)
+        return fail(DS_ERR_ARG, "ds_returns: reward_tr/Ni_tr/finished_tr/returns/advantage must be non-NULL");
+    if (h->n > 256) return fail(DS_ERR_ARG, "ds_returns: n_agents > 256 is not supported");
+    if (io->T == 0) return DS_OK;
+    DeviceGuard guard(h->device);
+    ds::ReturnsArgs a;
+    a.E = h->E; a.n = h->n; a.k = h->k; a.T = io->T;
+    // CTAs of <= 128 threads (whole environments): enough CTAs to cover the SMs several times
+    int G = 128 / h->n;
+    G = G < 1 ? 1 : (G > h->E ? h->E : G);
+    while (G > 1 && (h->E + G - 1) / G < 4 * h->sm_count) G /= 2;
+    a.G = G;
+    a.discount = io->discount;
+    a.r_tr = io->reward_tr; a.base = io->baseline; a.Ni_tr = io->Ni_tr; a.fin_tr = io->finished_tr;
+    a.ret = io->returns; a.adv = io->advantage; a.cnt = io->count;
+    const int threads = ((G * h->n + 31) / 32) * 32;
+    const int blocks = (h->E + G - 1) / G;
+    const size_t smem = 2 * (size_t)G * h->n * h->real_bytes;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (h->real_bytes == 8) {
+        if (h->k == 2) ds::returns_kernel<double, 3><<<blocks, threads, smem, st>>>(a);
+        else ds::returns_kernel<double, 0><<<blocks, threads, smem, st>>>(a);
+    } else {
+        if (h->k == 2) ds::returns_kernel<float, 3><<<blocks, threads, smem, st>>>(a);
+        else ds::returns_kernel<float, 0><<<blocks, threads, smem, st>>>(a);
+    }
+    DS_CUDA(cudaGetLastError());
+    return DS_OK;
+}
+
 int ds_set_state(ds_handle *h, const double *state_host, const int32_t *t_host, const ds_buffers *io,
                  void *cuda_stream)
 {

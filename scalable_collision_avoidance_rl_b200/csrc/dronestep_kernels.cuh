@@ -1308,6 +1308,107 @@ rollout_kernel(const RolloutArgs ra)
     }
 }
 
+// ---------------------------------------------------------------- returns / advantages
+// SURVEY.md section 8f row 2 -- what the reference's learners do with the reward and Ni
+// trajectories of an episode (replaces the host-side ExperienceBuffers walk):
+//   returns     G_i(t) = G_i(t+1) * discount + r_i(t), G_i(last) = r_i(last)   (SAC_agents.py:304-310,
+//               108-113), multiply then add, unfused, backwards from the last executed step;
+//   advantages  A_i(t) = sum over j in N_i(t), in list order, of (G_j(t) - V_i(t))   (:333-345),
+//               V = the critic's baseline (0 when none is given).
+// One thread per agent walks its environment's episode backwards; the G of a step are exchanged
+// through shared memory (double buffered: one barrier per step).  Inputs are loaded U = 4 steps
+// at a time so that the memory latency is paid once per block of steps, not per step.  A step is
+// executed iff its finished code (ds_rollout: 0 running, 1 finished here, 2 not executed) is not
+// 2; not-executed steps get zeros.  HBM bound: 37 B per agent-step (f64, no baseline).
+struct ReturnsArgs {
+    int E, n, k, T, G;
+    double discount;
+    const void *r_tr, *base;
+    const int *Ni_tr;
+    const uint8_t *fin_tr;
+    void *ret, *adv;
+    uint8_t *cnt;
+};
+
+template <typename Real, int KP1>      // KP1 = k + 1 neighbour slots held in registers (0: any k)
+__global__ void __launch_bounds__(256) returns_kernel(const ReturnsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Real *sG = reinterpret_cast<Real *>(smem_raw);                 // [2][G * n]
+    constexpr int U = 4;
+    const int n = a.n, A = a.G * n, tid = threadIdx.x;
+    const int le = tid / n, i = tid - le * n;
+    const int e = blockIdx.x * a.G + le;
+    const bool active = tid < A && e < a.E;
+    const size_t EN = (size_t)a.E * n;
+    const size_t g = active ? (size_t)e * n + i : 0;
+    const int kp1 = (KP1 > 0) ? KP1 : a.k + 1;
+    const Real disc = (Real)a.discount;
+    const Real *r_tr = reinterpret_cast<const Real *>(a.r_tr);
+    const Real *base = reinterpret_cast<const Real *>(a.base);
+    Real *ret = reinterpret_cast<Real *>(a.ret), *adv = reinterpret_cast<Real *>(a.adv);
+    Real Gn = 0;
+    bool started = false;
+    int par = 0;
+    for (int tb = a.T; tb > 0; tb -= U) {                          // steps tb-1 .. tb-U (those >= 0)
+        Real r[U], v[U];
+        int code[U];
+        int nj[U][KP1 > 0 ? KP1 : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = tb - 1 - u;
+            code[u] = 2; r[u] = 0; v[u] = 0;
+            if (active && t >= 0) {
+                const size_t at = (size_t)t * EN + g;
+                code[u] = a.fin_tr[(size_t)t * a.E + e];
+                r[u] = r_tr[at];
+                if (base) v[u] = base[at];
+                if (KP1 > 0) {
+#pragma unroll
+                    for (int m = 0; m < (KP1 > 0 ? KP1 : 1); ++m) nj[u][m] = a.Ni_tr[at * KP1 + m];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = tb - 1 - u;
+            if (t < 0) break;                                      // uniform
+            const bool exec = active && code[u] != 2;
+            Real Gt = 0;
+            if (exec) {
+                Gt = started ? add_rn(mul_rn(Gn, disc), r[u]) : r[u];       // :306-309
+                Gn = Gt; started = true;
+            }
+            if (active) sG[par * A + tid] = Gt;
+            __syncthreads();
+            if (active) {
+                const size_t at = (size_t)t * EN + g;
+                Real sum = 0;                                               // :339
+                int c = 0;
+                if (exec) {
+                    const Real *sg = sG + par * A + le * n;
+                    if (KP1 > 0) {
+#pragma unroll
+                        for (int m = 0; m < (KP1 > 0 ? KP1 : 1); ++m) {
+                            const int j = nj[u][m];
+                            if (j >= 0) { sum = add_rn(sum, sub_rn(sg[j], v[u])); ++c; }   // :344-345
+                        }
+                    } else {
+                        for (int m = 0; m < kp1; ++m) {
+                            const int j = a.Ni_tr[at * kp1 + m];
+                            if (j >= 0) { sum = add_rn(sum, sub_rn(sg[j], v[u])); ++c; }
+                        }
+                    }
+                }
+                ret[at] = Gt;
+                adv[at] = sum;
+                if (a.cnt) a.cnt[at] = (uint8_t)c;
+            }
+            par ^= 1;
+        }
+    }
+}
+
 // Deterministic sum over environments of agg[E][4] -> out[0..3]; out[4] = E.
 __global__ void __launch_bounds__(1024) reduce_agg_kernel(const double *__restrict__ agg, int E,
                                                           double *__restrict__ out)

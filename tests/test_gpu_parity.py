@@ -390,6 +390,51 @@ def test_rollout_dense_and_large(n, E, grid, delta, box, k, hetero):
     assert torch.equal(z_last, env.z_states) and torch.equal(Ni_last, env.Ni)
 
 
+@pytest.mark.parametrize("name", ["returns_n5_seed0", "returns_n5_seed3_g0.9", "returns_n8_seed1"])
+def test_returns_vs_reference_golden(name):
+    """ds_returns on the reference's own episode: returns recorded from the reference's
+    TrainedAgent.benchmark_cirtic and advantage sums of its train_NN loop, bit-exact."""
+    import os
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    n, T = int(g["n"]), g["reward"].shape[0]
+    env = BatchedDrones(1, n, [5, 5], "O", int(g["k"]), np.ones(n), True, seed=0, warn=False)
+    dev = env.device
+    out = env.returns(torch.as_tensor(g["reward"][:, None, :], device=dev),
+                      torch.as_tensor(g["Ni"][:, None], device=dev),
+                      torch.as_tensor(g["finished"][:, None], device=dev),
+                      discount=float(g["discount"]), baseline=torch.as_tensor(g["baseline"][:, None, :], device=dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(out["returns"].cpu().numpy()[:, 0], g["returns"])
+    assert np.array_equal(out["advantage"].cpu().numpy()[:, 0], g["advantage"])
+    assert np.array_equal(out["count"].cpu().numpy()[:, 0], (g["Ni"] >= 0).sum(-1))
+
+
+@pytest.mark.parametrize("n,E,k,T", [(10, 4096, 2, 200), (5, 333, 2, 61), (32, 65, 2, 40), (7, 50, 4, 33), (128, 9, 2, 10)])
+def test_returns_on_rollout_vs_oracle(n, E, k, T):
+    """ds_rollout -> ds_returns on the device, against the oracle's restatement of the reference's
+    host-side walk over its ExperienceBuffers; includes episodes that end inside the rollout."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    grid = [5, 5] if n <= 10 else ([32, 32] if n <= 32 else [64, 64])
+    rng = np.random.default_rng(n + E)
+    env = BatchedDrones(E, n, grid, "O", k, np.ones(n), True, seed=4, warn=False)
+    st, _ = env.get_state()
+    env.set_state(st, rng.integers(max(0, 200 - 2 * T), 200, E).astype(np.int32))   # some hit the time limit
+    tab = formation.unit_action_table(16)
+    act = tab[rng.integers(0, 16, (T, E, n))]
+    ro = env.rollout(actions=torch.as_tensor(act, device=env.device), record=("reward", "obs", "finished"))
+    base = torch.as_tensor(rng.standard_normal((T, E, n)), device=env.device)
+    out = env.returns(ro["reward"], ro["Ni"], ro["finished"], discount=0.95, baseline=base)
+    torch.cuda.synchronize()
+    fin = ro["finished"].cpu().numpy()
+    assert (fin == 2).any() and (fin == 1).any()
+    G, adv, cnt = c_oracle.returns(ro["reward"].cpu().numpy(), ro["Ni"].cpu().numpy(), fin, 0.95,
+                                   base.cpu().numpy())
+    assert np.array_equal(out["returns"].cpu().numpy(), G)
+    assert np.array_equal(out["advantage"].cpu().numpy(), adv)
+    assert np.array_equal(out["count"].cpu().numpy(), cnt)
+
+
 def test_error_behaviour():
     from scalable_collision_avoidance_rl_b200 import BatchedDrones, DroneStepError
     with pytest.raises(DroneStepError):

@@ -107,3 +107,56 @@ def test_known_answer_facts():
     assert abs(b * 9.99e3 - 99.9) < 1e-12
     goal0 = q * np.sum((g["end_points"].reshape(-1, 2)[0] - out.pos[0, 0]) ** 2)
     assert -out.r[0, 0] >= goal0 + 99.9 - 1e-9
+
+
+RETURNS = ["returns_n5_seed0", "returns_n5_seed3_g0.9", "returns_n8_seed1"]
+
+
+@pytest.mark.parametrize("name", RETURNS)
+def test_returns_oracles_match_reference(name):
+    """Monte-Carlo returns (computed by the reference's own TrainedAgent.benchmark_cirtic) and the
+    Delta-neighbourhood advantage sums (reference loop SAC_agents.py:333-345 on the reference's
+    buffers and critics), recorded by oracle/make_golden_returns.py: both restatements bit-exact."""
+    import os
+    from oracle import np_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    r, Ni, fin = g["reward"][:, None, :], g["Ni"][:, None], g["finished"][:, None]
+    assert fin[-1, 0] == 1 and fin[:-1].sum() == 0                       # one whole episode
+    for mod in (c_oracle, np_oracle):
+        G, adv, cnt = mod.returns(r, Ni, fin, float(g["discount"]), g["baseline"][:, None, :])
+        assert np.array_equal(G[:, 0], g["returns"]), mod.__name__
+        assert np.array_equal(adv[:, 0], g["advantage"]), mod.__name__
+        assert np.array_equal(cnt[:, 0], (g["Ni"] >= 0).sum(-1))
+        G0, adv0, _ = mod.returns(r, Ni, fin, float(g["discount"]))       # no baseline: plain neighbour sums
+        assert np.array_equal(G0, G)
+        want = np.zeros_like(adv0[:, 0])
+        for m in range(g["Ni"].shape[-1]):
+            j = g["Ni"][..., m]
+            want = np.where(j >= 0, want + np.take_along_axis(g["returns"], np.where(j >= 0, j, 0), 1), want)
+        assert np.array_equal(adv0[:, 0], want)
+
+
+def test_returns_oracles_agree_on_ragged_batch():
+    """Batch of environments with different episode ends (finished codes 0/1/2 as ds_rollout
+    writes them, including environments that never ran): C and NumPy restatements agree."""
+    from oracle import np_oracle
+    rng = np.random.default_rng(5)
+    T, E, n, k = 37, 23, 6, 2
+    r = -rng.uniform(0, 30, (T, E, n))
+    Ni = rng.integers(-1, n, (T, E, n, k + 1)).astype(np.int32)
+    Ni[..., 0] = np.arange(n)
+    fin = np.zeros((T, E), np.uint8)
+    ends = rng.integers(0, T + 8, E)
+    for e in range(E):
+        if ends[e] < T:
+            fin[ends[e], e] = 1
+            fin[ends[e] + 1:, e] = 2
+    fin[:, 3] = 2                                                        # done before the rollout
+    base = rng.standard_normal((T, E, n))
+    a = c_oracle.returns(r, Ni, fin, 0.97, base)
+    b = np_oracle.returns(r, Ni, fin, 0.97, base)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert (a[0][:, 3] == 0).all() and (a[2][:, 3] == 0).all()
+    e = int(np.argmax(ends < T))
+    assert (a[0][ends[e] + 1:, e] == 0).all() and np.array_equal(a[0][ends[e], e], r[ends[e], e])
