@@ -1320,6 +1320,9 @@ rollout_kernel(const RolloutArgs ra)
 // at a time so that the memory latency is paid once per block of steps, not per step.  A step is
 // executed iff its finished code (ds_rollout: 0 running, 1 finished here, 2 not executed) is not
 // 2; not-executed steps get zeros.  HBM bound: 37 B per agent-step (f64, no baseline).
+#ifndef DS_RET_U
+#define DS_RET_U 4        // steps whose inputs are in flight together (U = 8: +10% at config 3, -18% at the HBM point)
+#endif
 struct ReturnsArgs {
     int E, n, k, T, G;
     double discount;
@@ -1335,7 +1338,7 @@ __global__ void __launch_bounds__(256) returns_kernel(const ReturnsArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Real *sG = reinterpret_cast<Real *>(smem_raw);                 // [2][G * n]
-    constexpr int U = 4;
+    constexpr int U = DS_RET_U;
     const int n = a.n, A = a.G * n, tid = threadIdx.x;
     const int le = tid / n, i = tid - le * n;
     const int e = blockIdx.x * a.G + le;
