@@ -136,6 +136,15 @@ void ds_default_params(ds_params *p);
 /* drones.step(actions) for E environments (drone_env.py:214-258). */
 int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p,
             const ds_buffers *io, void *cuda_stream);
+/* One CLOSED-LOOP step: every agent's action is computed on the device from the current state by
+ * one of the reference's baseline controllers, then the step proceeds as ds_step (the action taken
+ * is left in io->vel, as state[:,2:4] = u at drone_env.py:238).
+ *   DS_CTRL_PROPORTIONAL  proportional_control(state, env)        drone_env.py:655-679
+ *   DS_CTRL_GRADIENT      gradient_control(state, env, u_max)     drone_env.py:612-653 */
+#define DS_CTRL_PROPORTIONAL 1
+#define DS_CTRL_GRADIENT 2
+int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params *p,
+                    const ds_buffers *io, void *cuda_stream);
 /* rewards() on the current state without integrating: the call init_agents makes
  * after a reset (drone_env.py:208-210).  Leaves t / finished untouched. */
 int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream);

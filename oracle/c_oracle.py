@@ -61,6 +61,7 @@ def lib():
         _lib.oracle_step_batch.restype = ctypes.c_int
         _lib.oracle_rollout_batch.restype = ctypes.c_int
         _lib.oracle_returns_batch.restype = ctypes.c_int
+        _lib.oracle_control_batch.restype = ctypes.c_int
     return _lib
 
 
@@ -177,3 +178,21 @@ def returns(reward_tr, Ni_tr, finished_tr, discount, baseline=None):
     if rc != 0:
         raise ValueError(f"oracle_returns_batch failed rc={rc}")
     return G, adv, cnt
+
+
+CTRL_PROPORTIONAL, CTRL_GRADIENT = 1, 2
+
+
+def control(mode, pos, end_points, d_safety, radius=None, u_max=1.0):
+    """Baseline controllers of the reference (drone_env.py:612-679) for a batch of environments:
+    pos [E,n,2] -> actions [E,n,2].  mode: CTRL_PROPORTIONAL | CTRL_GRADIENT."""
+    pos = np.ascontiguousarray(np.asarray(pos, np.float64))
+    E, n, _ = pos.shape
+    xF = np.ascontiguousarray(np.asarray(end_points, np.float64).reshape(n, 2))
+    ds = np.ascontiguousarray(np.asarray(d_safety, np.float64).reshape(n))
+    rad = np.full(n, 0.1) if radius is None else np.ascontiguousarray(np.asarray(radius, np.float64).reshape(n))
+    act = np.zeros((E, n, 2))
+    rc = lib().oracle_control_batch(int(mode), E, n, _p(pos), _p(rad), _p(xF), _p(ds), ctypes.c_double(u_max), _p(act))
+    if rc != 0:
+        raise ValueError(f"oracle_control_batch failed rc={rc}")
+    return act

@@ -351,6 +351,54 @@ int oracle_rollout_batch(int E, int n, int k, int simplify, int T, const oracle_
     return 0;
 }
 
+/* ---------------------------------------------------------------- baseline controllers
+ * deterministic action sources of the reference.
+ *   proportional_control (drone_env.py:655-679): u = xF - x, norm capped at u_max = 1;
+ *   gradient_control     (drone_env.py:612-653): u = clip(-(2 (x - xF) - 0.1 sum_j push_ij), +-u_max),
+ *       push_ij = (x_i - x_j) / (d_ij * ||x_i - x_j||) for every j != i with
+ *       d_ij = ||x_i - x_j|| - l_i - l_j <= d_safety[i]   (no zero rule here: d_ij = 0 divides by zero).
+ * np.linalg.norm of a 1-D vector is sqrt(ddot(v, v)) = sqrt(fma(y, y, x * x)). */
+static void control_one(int mode, int n, const double *pos, const double *radius, const double *xF,
+                        const double *d_safety, double u_max, double *act)
+{
+    for (int i = 0; i < n; ++i) {
+        const double xi = pos[2 * i], yi = pos[2 * i + 1];
+        if (mode == 1) {                                             /* proportional_control */
+            double ux = 1 * (xF[2 * i] - xi), uy = 1 * (xF[2 * i + 1] - yi);          /* :669-671 */
+            const double nrm = norm2_blas(ux, uy);                                     /* :673 */
+            if (nrm > 1) { ux = ux / nrm * 1; uy = uy / nrm * 1; }                     /* :674-676 (u_max = 1) */
+            act[2 * i] = ux; act[2 * i + 1] = uy;
+        } else {                                                     /* gradient_control */
+            const double t1x = 2 * (xi - xF[2 * i]), t1y = 2 * (yi - xF[2 * i + 1]);   /* :636 */
+            double t2x = 0, t2y = 0;
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const double dx = xi - pos[2 * j], dy = yi - pos[2 * j + 1];
+                const double nrm = norm2_blas(dx, dy);
+                const double dij = nrm - radius[i] - radius[j];                        /* :644 */
+                if (dij <= d_safety[i]) {                                              /* :646 */
+                    const double den = dij * nrm;                                      /* :647 */
+                    t2x += dx / den; t2y += dy / den;
+                }
+            }
+            const double gx = 1 * t1x - 0.1 * t2x, gy = 1 * t1y - 0.1 * t2y;           /* :649 */
+            double ux = -gx, uy = -gy;                                                 /* :650 np.clip */
+            ux = ux < -u_max ? -u_max : (ux > u_max ? u_max : ux);
+            uy = uy < -u_max ? -u_max : (uy > u_max ? u_max : uy);
+            act[2 * i] = ux; act[2 * i + 1] = uy;
+        }
+    }
+}
+
+int oracle_control_batch(int mode, int E, int n, const double *pos, const double *radius, const double *xF,
+                         const double *d_safety, double u_max, double *act)
+{
+    if ((mode != 1 && mode != 2) || E < 1 || n < 1) return -1;
+    for (int e = 0; e < E; ++e)
+        control_one(mode, n, pos + (size_t)e * n * 2, radius, xF, d_safety, u_max, act + (size_t)e * n * 2);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- returns / advantages
  * what the learners do with the rollout's reward and Ni trajectories.
  *   returns     G_i(t) = G_i(t+1) * discount + r_i(t), G_i(last) = r_i(last)

@@ -135,3 +135,28 @@ def returns(reward_tr, Ni_tr, finished_tr, discount, baseline=None):
         adv = np.where(valid, adv + (gj - base), adv)
         cnt += valid
     return G, adv, cnt
+
+
+def control(mode, pos, end_points, d_safety, radius=None, u_max=1.0):
+    """NumPy restatement of proportional_control (mode 1, drone_env.py:655-679) and gradient_control
+    (mode 2, drone_env.py:612-653) over E environments; same contract as ``c_oracle.control``."""
+    pos = np.asarray(pos, np.float64)
+    E, n, _ = pos.shape
+    xF = np.asarray(end_points, np.float64).reshape(1, n, 2)
+    ds = np.asarray(d_safety, np.float64).reshape(1, n, 1)
+    rad = np.full(n, 0.1) if radius is None else np.asarray(radius, np.float64).reshape(n)
+    with np.errstate(all="ignore"):
+        if mode == 1:
+            u = 1 * (xF - pos)
+            nrm = _norm_blas(u[..., 0], u[..., 1])[..., None]
+            return np.where(nrm > 1, u / nrm * 1, u)
+        d = pos[:, :, None, :] - pos[:, None, :, :]                       # x_i - x_j
+        nrm = _norm_blas(d[..., 0], d[..., 1])
+        dij = nrm - rad[None, :, None] - rad[None, None, :]
+        use = (dij <= ds) & ~np.eye(n, dtype=bool)[None]
+        den = dij * nrm
+        t2 = np.zeros((E, n, 2))
+        for j in range(n):                                                # accumulation order of :640-647
+            t2 = np.where(use[:, :, j, None], t2 + d[:, :, j, :] / den[:, :, j, None], t2)
+        grad = 1 * (2 * (pos - xF)) - 0.1 * t2
+        return np.clip(-grad, -u_max, u_max)

@@ -15,12 +15,14 @@ c_void_p, c_int32, c_double = ctypes.c_void_p, ctypes.c_int32, ctypes.c_double
 
 DS_OK, DS_ERR_ARG, DS_ERR_CUDA, DS_ERR_NO_DEVICE = 0, -1, -2, -3
 DS_LOG_DIV, DS_LOG_DIFF = 0, 1
+DS_CTRL_PROPORTIONAL, DS_CTRL_GRADIENT = 1, 2
 DS_MAX_AGENTS, DS_MAX_K = 1024, 16
 
 EXPORTED_SYMBOLS = (
     "ds_abi_version", "ds_last_error", "ds_device_count", "ds_create", "ds_destroy",
     "ds_default_params", "ds_step", "ds_observe", "ds_rollout", "ds_reduce_aggregates",
     "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_rollout_host", "ds_returns",
+    "ds_step_control",
 )
 
 

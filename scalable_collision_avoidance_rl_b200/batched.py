@@ -189,6 +189,19 @@ class BatchedDrones:
         return ((self.pos, self.vel), self.z_states, self.rewards, self.n_collisions, self.finished,
                 self.true_rewards)
 
+    def step_control(self, controller="gradient", u_max=1.0):
+        """One closed-loop step: actions computed on the device by one of the reference's baseline
+        controllers (drone_env.py:612-679: "proportional" | "gradient"), then drones.step()
+        (ds_step_control).  Returns the same 6-tuple as step(); the action taken is self.vel."""
+        mode = {"proportional": _lib.DS_CTRL_PROPORTIONAL, "gradient": _lib.DS_CTRL_GRADIENT}.get(controller)
+        if mode is None:
+            raise ValueError("controller must be 'proportional' or 'gradient'")
+        p = self._params()
+        _lib.check(self.lib.ds_step_control(self._h, mode, ctypes.c_double(u_max), ctypes.byref(p),
+                                            ctypes.byref(self._io), self._stream()), "ds_step_control")
+        return ((self.pos, self.vel), self.z_states, self.rewards, self.n_collisions, self.finished,
+                self.true_rewards)
+
     def step_host(self, actions):
         """Same step with HOST arrays in and out (ds_step_host): one H2D, one kernel, D2H of the
         reference's 6-tuple into pinned buffers, one synchronise.  Returns numpy views."""

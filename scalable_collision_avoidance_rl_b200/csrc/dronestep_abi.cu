@@ -217,6 +217,7 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
         return fail(DS_ERR_ARG, "ds_buffers: finished/t must be non-NULL for a step");
     a->E = h->E; a->n = h->n; a->k = h->k; a->simplify = h->simplify; a->G = h->step_G;
     a->do_integrate = integrate ? 1 : 0;
+    a->ctrl = 0; a->u_max = 1.0;
     a->log_mode = p->log_mode;
     a->max_steps = p->max_time_steps;
     a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds, h->d_thr2, h->d_clipcnt, h->d_logtab};
@@ -417,6 +418,19 @@ int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p, const ds_
     ds::StepArgs a;
     if (int rc = fill_step_args(h, p, io, actions_dev, true, &a)) return rc;
     if (!actions_dev) return fail(DS_ERR_ARG, "ds_step: actions_dev is NULL");
+    DeviceGuard guard(h->device);
+    return launch_step(h, a, (cudaStream_t)cuda_stream);
+}
+
+int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params *p, const ds_buffers *io,
+                    void *cuda_stream)
+{
+    ds::StepArgs a;
+    if (int rc = fill_step_args(h, p, io, nullptr, true, &a)) return rc;
+    if (controller != DS_CTRL_PROPORTIONAL && controller != DS_CTRL_GRADIENT)
+        return fail(DS_ERR_ARG, "ds_step_control: controller must be DS_CTRL_PROPORTIONAL or DS_CTRL_GRADIENT");
+    if (!(u_max >= 0)) return fail(DS_ERR_ARG, "ds_step_control: u_max must be >= 0");
+    a.ctrl = controller; a.u_max = u_max;
     DeviceGuard guard(h->device);
     return launch_step(h, a, (cudaStream_t)cuda_stream);
 }

@@ -269,6 +269,8 @@ struct Consts {              // device arrays, length n (xF: 2n); Real typed unl
 
 struct StepArgs {
     int E, n, k, simplify, G, do_integrate, log_mode, max_steps;
+    int ctrl;                // 0: actions given; 1 / 2: the reference's proportional / gradient controller
+    double u_max;            // gradient controller's clip (drone_env.py:612)
     Consts c;
     double dt, q, b, goal_tol, sentinel, zero_eps, ghost;
     const void *act;         // Real [E][n][2]
@@ -669,6 +671,43 @@ DS_HD void eval_row_near32(RowResult<Real, K> &o, int n, int i, Real xi, Real yi
     row_end<Real, K>(o, acc, xi, yi, c, P);
 }
 
+// Baseline controllers of the reference for agent i of one frame:
+//   mode 1  proportional_control (drone_env.py:655-679): u = xF - x, norm capped at 1;
+//   mode 2  gradient_control (drone_env.py:612-653): u = clip(-(2 (x - xF) - 0.1 sum_j push_ij), +-u_max),
+//           push_ij = (x_i - x_j) / (d_ij ||x_i - x_j||) over j != i with d_ij = ||x_i - x_j|| - l_i - l_j
+//           <= d_safety[i] (global knowledge; no zero rule: d_ij = 0 divides by zero like the reference).
+// Same operation order as the reference (np.linalg.norm of a 1-D vector = sqrt(ddot) = sqrt(fma)).
+template <typename Real>
+DS_HD void control_action(int mode, int n, int i, Real xi, Real yi, Real xF, Real yF, Real ds_i, Real rad_i,
+                          const typename vec2_of<Real>::type *__restrict__ s_pos,
+                          const Real *__restrict__ s_radius, int cs, Real u_max, Real &ux, Real &uy)
+{
+    using V2 = typename vec2_of<Real>::type;
+    if (mode == 1) {
+        ux = sub_rn(xF, xi); uy = sub_rn(yF, yi);                                  // :669-671, k_gain = 1
+        const Real nrm = sqrt_rn(fma_rn(uy, uy, mul_rn(ux, ux)));                  // :673
+        if (nrm > (Real)1) { ux = div_rn(ux, nrm); uy = div_rn(uy, nrm); }         // :674-676, u_max = 1
+        return;
+    }
+    const Real t1x = mul_rn((Real)2, sub_rn(xi, xF)), t1y = mul_rn((Real)2, sub_rn(yi, yF));   // :636
+    Real t2x = 0, t2y = 0;
+    for (int j = 0; j < n; ++j) {
+        if (j == i) continue;
+        const V2 pj = s_pos[j];
+        const Real dx = sub_rn(xi, pj.x), dy = sub_rn(yi, pj.y);
+        const Real nrm = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));
+        const Real dij = sub_rn(sub_rn(nrm, rad_i), s_radius[j * cs]);             // :644
+        if (dij <= ds_i) {                                                         // :646
+            const Real den = mul_rn(dij, nrm);                                     // :647
+            t2x = add_rn(t2x, div_rn(dx, den)); t2y = add_rn(t2y, div_rn(dy, den));
+        }
+    }
+    const Real gx = sub_rn(t1x, mul_rn((Real)0.1, t2x)), gy = sub_rn(t1y, mul_rn((Real)0.1, t2y));   // :649
+    ux = -gx; uy = -gy;                                                            // :650 np.clip
+    ux = ux < -u_max ? -u_max : (ux > u_max ? u_max : ux);
+    uy = uy < -u_max ? -u_max : (uy > u_max ? u_max : uy);
+}
+
 // Write z_i (k+1 rows) and Ni_i (drone_env.py:344-397) for global agent index g.  The in-range
 // neighbours occupy slots 1..min(in_range, k) in order, so Ni[kth] is either tj[kth] or -1.
 template <typename Real, int K>
@@ -785,12 +824,25 @@ step_kernel(const StepArgs a)
 
     Real xi = 0, yi = 0;
     AgentConst<Real> c{};
+    V2 u_ctrl{};
+    if (a.ctrl) {
+        // closed loop: the action is a function of the CURRENT positions of the whole environment
+        if (active) sm.pos[lt] = reinterpret_cast<const V2 *>(a.pos)[g];
+        __syncthreads();
+        if (active) {
+            c = load_agent_const<Real>(a.c, i);
+            const V2 p = sm.pos[lt];
+            control_action<Real>(a.ctrl, n, i, p.x, p.y, c.xF, c.yF, c.ds, c.radius, sm.pos + le * n, sm.radius, 1,
+                                 (Real)a.u_max, u_ctrl.x, u_ctrl.y);
+        }
+        __syncthreads();                                   // everybody has read the old positions
+    }
     if (active) {
         c = load_agent_const<Real>(a.c, i);
         V2 p = reinterpret_cast<const V2 *>(a.pos)[g];
         V2 v;
         if (a.do_integrate) {
-            const V2 u = reinterpret_cast<const V2 *>(a.act)[g];
+            const V2 u = a.ctrl ? u_ctrl : reinterpret_cast<const V2 *>(a.act)[g];
             p.x = add_rn(p.x, mul_rn(P.dt, u.x));     // A = I, B = dt I (:78-79,235)
             p.y = add_rn(p.y, mul_rn(P.dt, u.y));
             v = u;                                     // :238

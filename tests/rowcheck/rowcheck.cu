@@ -96,6 +96,18 @@ static void run(int path, int n, int k, int simplify, int log_mode, const double
     for (size_t q = 0; q < zr.size(); ++q) z[q] = zr[q];
 }
 
+// control_action (baseline controllers) for one frame on the host
+extern "C" int rowcheck_control(int mode, int n, const double *pos, const double *xF, const double *dsf,
+                                const double *radius, double u_max, double *act)
+{
+    std::vector<double2> sp(n);
+    for (int i = 0; i < n; ++i) { sp[i].x = pos[2 * i]; sp[i].y = pos[2 * i + 1]; }
+    for (int i = 0; i < n; ++i)
+        ds::control_action<double>(mode, n, i, sp[i].x, sp[i].y, xF[2 * i], xF[2 * i + 1], dsf[i], radius[i],
+                                   sp.data(), radius, 1, u_max, act[2 * i], act[2 * i + 1]);
+    return 0;
+}
+
 extern "C" double rowcheck_log(double x)
 {
     static std::vector<ds::LogTabEntry> tab;

@@ -435,6 +435,52 @@ def test_returns_on_rollout_vs_oracle(n, E, k, T):
     assert np.array_equal(out["count"].cpu().numpy(), cnt)
 
 
+@pytest.mark.parametrize("name,ctrl", [("control_gradient_n5", "gradient"), ("control_gradient_n10", "gradient"),
+                                       ("control_proportional_n8", "proportional")])
+def test_closed_loop_controller_vs_reference_golden(name, ctrl):
+    """ds_step_control free-running a whole closed-loop episode that the reference's own controller
+    drove in the reference's environment: actions and state bit-exact at every step, rewards to
+    1e-9, collision counts and the finishing step exact.  E copies of the episode run side by side."""
+    import os
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    n, E, T = int(g["n"]), 7, g["action"].shape[0]
+    env = BatchedDrones(E, n, [float(x) for x in g["grid"]], "O", 2, np.ones(n) * float(g["delta"]), True,
+                        seed=0, warn=False)
+    assert np.array_equal(env.end_points, g["end_points"]) and np.array_equal(env.d_safety, g["d_safety"])
+    env.set_state(np.broadcast_to(g["state_in"][0], (E, n, 5)).copy(), np.zeros(E, np.int32))
+    for t in range(T):
+        (pos, vel), z, r, ncoll, fin, tr = env.step_control(ctrl, u_max=float(g["u_max"]))
+        torch.cuda.synchronize()
+        for e in (0, E - 1):
+            assert np.array_equal(vel[e].cpu().numpy(), g["action"][t]), f"action t={t}"
+            assert np.array_equal(pos[e].cpu().numpy(), g["state"][t][:, 0:2]), f"state t={t}"
+            assert_close(r[e].cpu().numpy(), g["r"][t], FP64_TOL, f"r t={t}")
+            assert int(ncoll[e]) == int(g["ncoll"][t]) and bool(fin[e]) == bool(g["finished"][t])
+    assert bool(g["finished"][-1])
+
+
+def test_controllers_vs_oracle_dense_batch():
+    """Both controllers on dense random batches (many pairs inside d_safety) against the oracle,
+    through the closed-loop step: the action taken is left in vel."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    for n, E, box in ((10, 513, 2.0), (33, 40, 6.0), (128, 6, 20.0)):
+        rng = np.random.default_rng(n)
+        grid = [5, 5] if n <= 10 else [32, 32] if n <= 33 else [64, 64]
+        env = BatchedDrones(E, n, grid, "O", 2, np.ones(n), True, seed=1, warn=False)
+        pos = rng.uniform(0, box, (E, n, 2))
+        state = np.concatenate([pos, np.zeros((E, n, 2)), np.full((E, n, 1), 0.1)], 2)
+        for mode, ctrl, um in ((c_oracle.CTRL_GRADIENT, "gradient", 0.8), (c_oracle.CTRL_PROPORTIONAL, "proportional", 1.0)):
+            env.set_state(state, np.zeros(E, np.int32))
+            want = c_oracle.control(mode, pos, env.end_points, env.d_safety, None, um)
+            (p2, vel), *_ = env.step_control(ctrl, u_max=um)
+            torch.cuda.synchronize()
+            assert np.array_equal(vel.cpu().numpy(), want, equal_nan=True), (n, ctrl)
+            assert np.array_equal(p2.cpu().numpy(), pos + 0.05 * want, equal_nan=True)
+    with pytest.raises(ValueError):
+        env.step_control("pid")
+
+
 def test_error_behaviour():
     from scalable_collision_avoidance_rl_b200 import BatchedDrones, DroneStepError
     with pytest.raises(DroneStepError):

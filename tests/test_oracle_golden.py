@@ -160,3 +160,18 @@ def test_returns_oracles_agree_on_ragged_batch():
     assert (a[0][:, 3] == 0).all() and (a[2][:, 3] == 0).all()
     e = int(np.argmax(ends < T))
     assert (a[0][ends[e] + 1:, e] == 0).all() and np.array_equal(a[0][ends[e], e], r[ends[e], e])
+
+
+@pytest.mark.parametrize("name,key,mode", [("control_gradient_n5", "action", 2), ("control_gradient_n10", "action", 2),
+                                           ("control_proportional_n8", "action", 1),
+                                           ("control_dense_n7", "gradient", 2), ("control_dense_n7", "proportional", 1)])
+def test_control_oracles_match_reference(name, key, mode):
+    """Baseline controllers: C and NumPy restatements against the actions recorded from the
+    reference's gradient_control / proportional_control (drone_env.py:612-679), bit-exact."""
+    import os
+    from oracle import np_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    u_max = float(g["u_max"]) if mode == 2 else 1.0
+    for mod in (c_oracle, np_oracle):
+        act = mod.control(mode, g["state_in"][:, :, 0:2], g["end_points"], g["d_safety"], None, u_max)
+        assert np.array_equal(act, g[key], equal_nan=True), mod.__name__

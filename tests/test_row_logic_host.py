@@ -138,3 +138,23 @@ def test_table_log_accuracy(rowlib):
         assert rowlib.rowcheck_log(0.0) == -np.inf and np.isnan(rowlib.rowcheck_log(-1.0))
         assert rowlib.rowcheck_log(np.inf) == np.inf and np.isnan(rowlib.rowcheck_log(np.nan))
         assert abs(rowlib.rowcheck_log(5e-324) - np.log(5e-324)) < 1e-12
+
+
+@pytest.mark.parametrize("name,key,mode", [("control_gradient_n5", "action", 2), ("control_gradient_n10", "action", 2),
+                                           ("control_proportional_n8", "action", 1),
+                                           ("control_dense_n7", "gradient", 2), ("control_dense_n7", "proportional", 1)])
+def test_control_action_matches_reference(rowlib, name, key, mode):
+    """control_action (dronestep_kernels.cuh, host build) against the actions the reference's own
+    gradient_control / proportional_control produced (oracle/make_golden_control.py): bit-exact,
+    NaN patterns (division by zero at exact contact, agent on its goal) included."""
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    n = int(g["n"])
+    xF = np.ascontiguousarray(g["end_points"].reshape(-1)); dsf = np.ascontiguousarray(g["d_safety"])
+    rad = np.full(n, 0.1)
+    u_max = float(g["u_max"]) if mode == 2 else 1.0
+    for f in range(g["state_in"].shape[0]):
+        pos = np.ascontiguousarray(g["state_in"][f, :, 0:2])
+        act = np.zeros((n, 2))
+        rowlib.rowcheck_control(mode, n, *[x.ctypes.data_as(ctypes.c_void_p) for x in (pos, xF, dsf, rad)],
+                                ctypes.c_double(u_max), act.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(act, g[key][f], equal_nan=True), f"frame {f}"
