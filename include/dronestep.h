@@ -145,6 +145,11 @@ int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p,
 #define DS_CTRL_GRADIENT 2
 int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params *p,
                     const ds_buffers *io, void *cuda_stream);
+/* T closed-loop steps in one launch (the episode loop with `actions = gradient_control(state, env)`,
+ * train_problem.py:89-90): ro->actions / action_idx are ignored, everything else -- trajectory
+ * buffers, finished codes, agg, done -- as in ds_rollout. */
+int ds_rollout_control(ds_handle *h, int controller, double u_max, const ds_params *p,
+                       const ds_buffers *io, const ds_rollout_io *ro, void *cuda_stream);
 /* rewards() on the current state without integrating: the call init_agents makes
  * after a reset (drone_env.py:208-210).  Leaves t / finished untouched. */
 int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream);

@@ -274,6 +274,46 @@ class BatchedDrones:
         out["agg"], out["done"] = self.agg, self.done
         return out
 
+    def rollout_control(self, T, controller="gradient", u_max=1.0,
+                        record=("reward", "true_reward", "ncoll", "finished"), out=None):
+        """T closed-loop steps in ONE launch (ds_rollout_control): actions from the reference's
+        baseline controller on the current state at every step (train_problem.py:89-90 with
+        drone_env.py:612-679), state resident on chip.  Same outputs as rollout()."""
+        mode = {"proportional": _lib.DS_CTRL_PROPORTIONAL, "gradient": _lib.DS_CTRL_GRADIENT}.get(controller)
+        if mode is None:
+            raise ValueError("controller must be 'proportional' or 'gradient'")
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        out = {} if out is None else out
+        dev, dt_ = self.device, self.dtype
+
+        def buf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+
+        rec = set(record)
+        ro = _lib.ds_rollout_io()
+        ro.T = int(T)
+        if "pos" in rec: ro.pos_tr = buf("pos", (T, E, n, 2), dt_).data_ptr()
+        if "vel" in rec: ro.vel_tr = buf("vel", (T, E, n, 2), dt_).data_ptr()
+        if "reward" in rec: ro.reward_tr = buf("reward", (T, E, n), dt_).data_ptr()
+        if "true_reward" in rec: ro.true_reward_tr = buf("true_reward", (T, E, n), dt_).data_ptr()
+        if "obs" in rec:
+            ro.z_tr = buf("z", (T, E, n, k + 1, self.cols), dt_).data_ptr()
+            ro.Ni_tr = buf("Ni", (T, E, n, k + 1), torch.int32).data_ptr()
+        if "ncoll" in rec: ro.ncoll_tr = buf("ncoll", (T, E), torch.int32).data_ptr()
+        if "finished" in rec: ro.finished_tr = buf("finished", (T, E), torch.uint8).data_ptr()
+        ro.agg = self.agg.data_ptr()
+        ro.done = self.done.data_ptr()
+        p = self._params()
+        _lib.check(self.lib.ds_rollout_control(self._h, mode, ctypes.c_double(u_max), ctypes.byref(p),
+                                               ctypes.byref(self._io), ctypes.byref(ro), self._stream()),
+                   "ds_rollout_control")
+        out["agg"], out["done"] = self.agg, self.done
+        return out
+
     def rollout_host(self, actions=None, action_idx=None, action_table=None,
                      record=("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished"),
                      chunk=0, out=None):

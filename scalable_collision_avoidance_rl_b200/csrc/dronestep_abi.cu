@@ -435,6 +435,33 @@ int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params 
     return launch_step(h, a, (cudaStream_t)cuda_stream);
 }
 
+int ds_rollout_control(ds_handle *h, int controller, double u_max, const ds_params *p, const ds_buffers *io,
+                       const ds_rollout_io *ro, void *cuda_stream)
+{
+    ds::RolloutArgs ra;
+    std::memset(&ra, 0, sizeof ra);
+    if (int rc = fill_step_args(h, p, io, nullptr, true, &ra.s)) return rc;
+    if (controller != DS_CTRL_PROPORTIONAL && controller != DS_CTRL_GRADIENT)
+        return fail(DS_ERR_ARG, "ds_rollout_control: controller must be DS_CTRL_PROPORTIONAL or DS_CTRL_GRADIENT");
+    if (!(u_max >= 0)) return fail(DS_ERR_ARG, "ds_rollout_control: u_max must be >= 0");
+    if (!ro) return fail(DS_ERR_ARG, "ds_rollout_control: ds_rollout_io is NULL");
+    if (ro->T < 0) return fail(DS_ERR_ARG, "ds_rollout_control: T < 0");
+    if (!ro->agg || !ro->done) return fail(DS_ERR_ARG, "ds_rollout_control: agg/done must be non-NULL");
+    if ((ro->z_tr == nullptr) != (ro->Ni_tr == nullptr))
+        return fail(DS_ERR_ARG, "ds_rollout_control: z_tr and Ni_tr must be given together");
+    ra.s.ctrl = controller; ra.s.u_max = u_max;
+    ra.T = ro->T;
+    ra.pos_tr = ro->pos_tr; ra.vel_tr = ro->vel_tr; ra.r_tr = ro->reward_tr; ra.tr_tr = ro->true_reward_tr;
+    ra.z_tr = ro->z_tr; ra.Ni_tr = ro->Ni_tr; ra.ncoll_tr = ro->ncoll_tr; ra.fin_tr = ro->finished_tr;
+    ra.agg = ro->agg; ra.done = ro->done;
+    if (ro->T == 0) return DS_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const Geom gm{h->step_blocks, h->step_threads, h->step_smem};
+    if (h->real_bytes == 8) { DS_DISPATCH_NT(rollout_control_kernel, double, ra, gm) }
+    else { DS_DISPATCH_NT(rollout_control_kernel, float, ra, gm) }
+}
+
 int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream)
 {
     ds::StepArgs a;

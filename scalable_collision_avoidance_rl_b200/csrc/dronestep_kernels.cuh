@@ -878,6 +878,128 @@ step_kernel(const StepArgs a)
     }
 }
 
+// ---------------------------------------------------------------- closed-loop rollout kernel
+// T closed-loop steps in ONE launch: every step's action comes from one of the reference's
+// baseline controllers (control_action) evaluated on the CURRENT state, so the steps of an
+// environment are sequential and the time-parallel chunks of rollout_kernel do not apply; a CTA
+// owns G whole environments, keeps their state on chip for the whole call and loops over time
+// (five barriers per step, no launch or host round trip in between).  Recording, finished codes,
+// done flags and episode sums follow ds_rollout.
+template <typename Real, int K, int NT>
+__global__ void __launch_bounds__(NT)
+rollout_control_kernel(const RolloutArgs ra)
+{
+    using V2 = typename vec2_of<Real>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const StepArgs &a = ra.s;
+    const int n = a.n, G = a.G, T = ra.T;
+    CtaSmem<Real> sm(smem_raw, n, G, 1);
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        sm.delta[idx] = ((const Real *)a.c.delta)[idx];
+        sm.radius[idx] = ((const Real *)a.c.radius)[idx];
+    }
+    const ParamsR<Real> P(a);
+    const int kk = (K >= 0) ? K : a.k;
+    const int cols = a.simplify ? 2 : 5;
+    const int lt = threadIdx.x;
+    const int le = lt / n, i = lt - le * n;
+    const long long e = (long long)blockIdx.x * G + le;
+    const bool active = (lt < G * n) && (e < a.E);
+    const size_t g = active ? (size_t)e * n + i : 0;
+    const size_t EN = (size_t)a.E * n;
+    AgentConst<Real> c{};
+    V2 p{}, v{};
+    if (active) {
+        c = load_agent_const<Real>(a.c, i);
+        p = reinterpret_cast<const V2 *>(a.pos)[g];
+        v = reinterpret_cast<const V2 *>(a.vel)[g];
+        if (i == 0) { sm.alive[le] = (ra.done[e] == 0) ? 1 : 0; sm.tenv[le] = a.t[e]; sm.nexec[le] = 0; }
+    }
+    Real sum_r = 0, sum_tr = 0;
+    int sum_c = 0;
+    for (int step = 0; step < T; ++step) {
+        if (active) sm.pos[lt] = p;
+        __syncthreads();                                   // current positions, alive / t of this step
+        const bool alive = active && sm.alive[le] != 0;
+        V2 u{};
+        if (alive)
+            control_action<Real>(a.ctrl, n, i, p.x, p.y, c.xF, c.yF, c.ds, c.radius, sm.pos + le * n, sm.radius, 1,
+                                 (Real)a.u_max, u.x, u.y);
+        __syncthreads();                                   // everybody has read the old positions
+        if (alive) {
+            p.x = add_rn(p.x, mul_rn(P.dt, u.x));          // A = I, B = dt I (:78-79,235)
+            p.y = add_rn(p.y, mul_rn(P.dt, u.y));
+            v = u;                                         // :238
+            sm.pos[lt] = p;
+            sm.act[lt] = v;
+            if (i == 0) { sm.cnt[le] = 0; sm.notgoal[le] = 0; }
+        }
+        __syncthreads();
+        RowResult<Real, K> o;
+        const size_t at = (size_t)step * EN + g;
+        if (alive) {
+            eval_row<Real, K>(o, n, i, p.x, p.y, c, sm.pos + le * n, sm.delta, sm.radius, P, a.c.logtab);
+            if (o.ncoll) atomicAdd(&sm.cnt[le], o.ncoll);
+            if (!o.at_goal) sm.notgoal[le] = 1;
+            if (ra.pos_tr) reinterpret_cast<V2 *>(ra.pos_tr)[at] = p;
+            if (ra.vel_tr) reinterpret_cast<V2 *>(ra.vel_tr)[at] = v;
+            if (ra.r_tr) reinterpret_cast<Real *>(ra.r_tr)[at] = o.r;
+            if (ra.tr_tr) reinterpret_cast<Real *>(ra.tr_tr)[at] = o.tr;
+            if (ra.z_tr)
+                write_obs<Real, K>(o, i, p.x, p.y, c, sm.pos + le * n, sm.act + le * n, sm.radius, P,
+                                   reinterpret_cast<Real *>(ra.z_tr), ra.Ni_tr, at);
+            sum_r = add_rn(sum_r, o.r); sum_tr = add_rn(sum_tr, o.tr);
+        }
+        __syncthreads();                                   // collision count / not-at-goal complete
+        const size_t fe = (size_t)step * a.E + (size_t)e;
+        if (alive) {
+            const int nc = sm.cnt[le];
+            const int tt = sm.tenv[le];
+            const bool fin = (sm.notgoal[le] == 0) || (tt >= a.max_steps - 1);        // :248-254
+            if (fin || step == T - 1) {
+                // last executed step of the call: the step()-style outputs in the live buffers
+                reinterpret_cast<Real *>(a.r)[g] = o.r;
+                reinterpret_cast<Real *>(a.tr)[g] = o.tr;
+                write_obs<Real, K>(o, i, p.x, p.y, c, sm.pos + le * n, sm.act + le * n, sm.radius, P,
+                                   reinterpret_cast<Real *>(a.z), a.Ni, g);
+            }
+            if (i == 0) {
+                sum_c += nc;
+                if (ra.ncoll_tr) ra.ncoll_tr[fe] = nc;
+                if (ra.fin_tr) ra.fin_tr[fe] = fin ? 1 : 0;
+                if (fin || step == T - 1) { a.ncoll[e] = nc; a.fin[e] = fin ? 1 : 0; }
+            }
+        } else if (active && i == 0 && ra.fin_tr) {
+            ra.fin_tr[fe] = 2;
+        }
+        __syncthreads();                                   // every row has read alive / t / flags of this step
+        if (alive && i == 0) {
+            const bool fin = (sm.notgoal[le] == 0) || (sm.tenv[le] >= a.max_steps - 1);
+            sm.tenv[le] += 1;                              // :256
+            sm.nexec[le] += 1;
+            if (fin) sm.alive[le] = 0;
+        }
+    }
+    // final state, episode sums (reduced per environment in a fixed order), done flags
+    __syncthreads();
+    if (active) {
+        reinterpret_cast<V2 *>(a.pos)[g] = p;
+        reinterpret_cast<V2 *>(a.vel)[g] = v;
+        sm.r[lt] = sum_r; sm.tr[lt] = sum_tr;
+    }
+    __syncthreads();
+    if (active && i == 0) {
+        a.t[e] = sm.tenv[le];
+        if (sm.nexec[le] > 0) {
+            if (sm.alive[le] == 0) ra.done[e] = 1;
+            double sr = 0, st = 0;
+            for (int j = 0; j < n; ++j) { sr += (double)sm.r[le * n + j]; st += (double)sm.tr[le * n + j]; }
+            double *ag4 = ra.agg + (size_t)e * 4;
+            ag4[0] += sr / n; ag4[1] += st / n; ag4[2] += (double)sum_c; ag4[3] += (double)sm.nexec[le];
+        }
+    }
+}
+
 // ---------------------------------------------------------------- rollout kernel
 // Shared memory of a rollout CTA.  Per CTA: constants [n], log table, work list [L].  Per row
 // (I = TC*G*n), double buffered over chunks: action, position.  Per agent of a slice

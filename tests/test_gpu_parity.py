@@ -460,6 +460,47 @@ def test_closed_loop_controller_vs_reference_golden(name, ctrl):
     assert bool(g["finished"][-1])
 
 
+@pytest.mark.parametrize("ctrl,n,E,grid", [("gradient", 10, 4096, [5, 5]), ("proportional", 5, 300, [5, 5]),
+                                          ("gradient", 32, 64, [32, 32])])
+def test_closed_loop_rollout_equals_stepping(ctrl, n, E, grid):
+    """ds_rollout_control (T closed-loop steps in one launch) == T x ds_step_control, bit for bit:
+    trajectories, finished codes (episodes end inside the call: the controllers reach the goals),
+    final state, done flags; episode sums to 1e-9."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    T = 130
+    a = BatchedDrones(E, n, grid, "O", 2, np.ones(n), True, seed=6, warn=False)
+    b = BatchedDrones(E, n, grid, "O", 2, np.ones(n), True, seed=6, warn=False)
+    assert torch.equal(a.pos, b.pos)
+    if n == 32:                                   # far goals: let the 200-step limit end the episodes
+        st, _ = a.get_state()
+        t0 = np.random.default_rng(0).integers(100, 190, E).astype(np.int32)
+        a.set_state(st, t0); b.set_state(st, t0)
+    rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
+    out = a.rollout_control(T, ctrl, u_max=1.0, record=rec)
+    torch.cuda.synchronize()
+    fin_tr = out["finished"].cpu().numpy()
+    done = np.zeros(E, bool)
+    sums = np.zeros((E, 4))
+    for t in range(T):
+        before = (b.pos.clone(), b.vel.clone(), b.internal_t.clone())
+        (pos, vel), z, r, nc, fin, tr = b.step_control(ctrl, u_max=1.0)
+        torch.cuda.synchronize()
+        d = torch.as_tensor(done, device=b.device)
+        b.pos[d] = before[0][d]; b.vel[d] = before[1][d]; b.internal_t[d] = before[2][d]   # finished envs freeze
+        lv = torch.as_tensor(~done, device=b.device)
+        assert np.array_equal(fin_tr[t][~done], fin.cpu().numpy()[~done]) and (fin_tr[t][done] == 2).all()
+        for key, val in (("pos", pos), ("vel", vel), ("reward", r), ("true_reward", tr), ("z", z), ("Ni", b.Ni), ("ncoll", nc)):
+            assert torch.equal(out[key][t][lv], val[lv]), f"{key} t={t}"
+        live = ~done
+        sums[live, 0] += r.cpu().numpy()[live].mean(1); sums[live, 1] += tr.cpu().numpy()[live].mean(1)
+        sums[live, 2] += nc.cpu().numpy()[live]; sums[live, 3] += 1
+        done |= fin.cpu().numpy().astype(bool) & live
+    assert done.any()
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.internal_t, b.internal_t)
+    assert np.array_equal(out["done"].cpu().numpy().astype(bool), done)
+    assert_close(out["agg"].cpu().numpy(), sums, 1e-9, "episode sums")
+
+
 def test_controllers_vs_oracle_dense_batch():
     """Both controllers on dense random batches (many pairs inside d_safety) against the oracle,
     through the closed-loop step: the action taken is left in vel."""
