@@ -6,8 +6,8 @@
 
 A "step" is one environment step of the whole batch (E environments x n agents), i.e.
 one pass of the hot path.  Steps are executed as fused rollout launches of one episode
-(<= 200 steps, reference drone_env.py:30) each; every episode starts from a fresh lattice
-reset staged on the device, reads its action stream from HBM and writes the full
+(<= 200 steps, reference drone_env.py:30) each; every episode starts from a fresh random lattice
+reset drawn on the device (ds_reset_random), reads its action stream from HBM and writes the full
 per-step outputs (state, rewards, observations, neighbour lists, collision counts,
 finished flags) to HBM trajectory buffers.
 
@@ -263,11 +263,13 @@ def run_ours(args, wl):
     per_launch_ms = []
     stream = torch.cuda.current_stream(dev)
 
+    ep_base = [0]
+
     def episode(ep, steps, timed):
-        # env.reset() with device-staged starts (drone_env.py:98-102): state, t, done, aggregates
+        # env.reset() on the device (drone_env.py:98-102,193-210): fresh distinct lattice nodes per
+        # environment (Philox stream = episode number), zero velocity, t = 0, initial observation
         b = ep % n_ep_bufs
-        env.pos.copy_(starts[b]); env.vel.zero_(); env.internal_t.zero_(); env.done.zero_(); env.agg.zero_()
-        env.observe(); launches[0] += 1                      # init_agents -> rewards() (:208)
+        env.reset_random(seed=1234 + rank, stream=ep_base[0] + ep); launches[0] += 2
         if timed:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -286,6 +288,7 @@ def run_ours(args, wl):
             s = min(T, left)
             episode(ep, s, timed)
             left -= s; ep += 1
+        ep_base[0] += ep
 
     def barrier():
         if world > 1:
@@ -372,7 +375,7 @@ def run_ours(args, wl):
         "config": {"workload": args.workload, "n_agents": n, "n_envs_per_gpu": E, "grid": grid,
                    "delta": wl["delta"], "k_closest": K_CLOSEST, "simplify_zstate": True,
                    "actions": f"uniform over {N_ACTIONS} unit directions, streamed from HBM",
-                   "episode_steps": T, "reset": "fresh lattice start per episode (device-staged)",
+                   "episode_steps": T, "reset": "fresh lattice start per episode (ds_reset_random on the device)",
                    "l2": f"inputs larger than L2: {alg_bytes_launch / 1e6:.0f} MB streamed per launch",
                    "log_mode": args.log_mode},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

@@ -193,6 +193,15 @@ int ds_get_state(ds_handle *h, double *state_host, int32_t *t_host,
 int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p,
              const ds_buffers *io, void *cuda_stream);
 
+/* env.reset() with the start drawn ON THE DEVICE: n distinct nodes of the d0 x d1 lattice
+ * {(idx * pitch, jdx * pitch)} per environment, uniformly and in order -- the distribution of
+ * random.sample(possible_coord, n_agents) at drone_env.py:193-205 (d0, d1 = floor(grid / pitch),
+ * pitch = 2 * 1.1 * l).  Counter-based (Philox4x32-10): the result depends only on (seed, stream,
+ * environment index), not on launch geometry; use a new `stream` per episode.  Zero velocity,
+ * t = 0, finished = 0, then ds_observe.  No host round trip, no synchronisation. */
+int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, int32_t d1, double pitch,
+                    const ds_params *p, const ds_buffers *io, void *cuda_stream);
+
 /* One step with HOST action / result buffers holding Real of the handle's
  * precision (pinned memory recommended): H2D actions -> ds_step -> D2H of the
  * reference's 6-tuple (drone_env.py:258), then one stream synchronise.  Output

@@ -160,3 +160,39 @@ def control(mode, pos, end_points, d_safety, radius=None, u_max=1.0):
             t2 = np.where(use[:, :, j, None], t2 + d[:, :, j, :] / den[:, :, j, None], t2)
         grad = 1 * (2 * (pos - xF)) - 0.1 * t2
         return np.clip(-grad, -u_max, u_max)
+
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    M = 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M, p1 & M, ((p0 >> 32) ^ c3 ^ k1) & M, p0 & M
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return [c0, c1, c2, c3]
+
+
+def reset_random(n_envs, n_agents, d0, d1, pitch, seed, stream):
+    """Restatement of the device-side reset sampler (reset_random_kernel): Philox4x32-10 keyed by
+    the seed, counter (environment, draw block, stream); Lemire's unbiased index; duplicates
+    redrawn.  Returns [E,n,2] float64 lattice coordinates [idx * pitch, jdx * pitch]
+    (reference drone_env.py:193-205 fixes the lattice and the distribution, not the stream)."""
+    L = d0 * d1
+    thresh = ((1 << 32) - L) % L
+    out = np.zeros((n_envs, n_agents, 2))
+    for e in range(n_envs):
+        picks, block, rnd = [], 0, []
+        while len(picks) < n_agents:
+            if not rnd:
+                rnd = _philox4x32_10(e, block, stream, 0, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+                block += 1
+            m = rnd.pop(0) * L
+            if (m & 0xFFFFFFFF) < thresh:
+                continue
+            node = m >> 32
+            if node in picks:
+                continue
+            picks.append(node)
+        nodes = np.array(picks)
+        out[e, :, 0] = (nodes // d1) * pitch
+        out[e, :, 1] = (nodes % d1) * pitch
+    return out

@@ -142,6 +142,19 @@ class BatchedDrones:
         self.done.zero_()
         self.agg.zero_()
 
+    def reset_random(self, seed=0, stream=0):
+        """drones.reset() with the start drawn on the device (ds_reset_random): distinct lattice
+        nodes per environment from Philox(seed; environment, stream) -- the distribution of the
+        reference's random.sample (drone_env.py:193-205), not its stream.  No host round trip;
+        pass a new `stream` (e.g. the episode number) for every reset."""
+        d0, d1 = formation.lattice_shape(self.grid)
+        p = self._params()
+        _lib.check(self.lib.ds_reset_random(self._h, ctypes.c_uint64(int(seed)), ctypes.c_uint32(int(stream)),
+                                            d0, d1, ctypes.c_double(formation.LATTICE_PITCH), ctypes.byref(p),
+                                            ctypes.byref(self._io), self._stream()), "ds_reset_random")
+        self.done.zero_()
+        self.agg.zero_()
+
     def observe(self):
         """rewards() on the current state (drone_env.py:208): refresh z_states/Ni/rewards."""
         p = self._params()

@@ -636,6 +636,31 @@ int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p, const ds_
     return ds_observe(h, p, io, cuda_stream);
 }
 
+int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, int32_t d1, double pitch,
+                    const ds_params *p, const ds_buffers *io, void *cuda_stream)
+{
+    if (!h || !io || !io->pos || !io->vel) return fail(DS_ERR_ARG, "ds_reset_random: NULL argument");
+    if (d0 < 1 || d1 < 1 || (long long)d0 * d1 > 0x7fffffffLL)
+        return fail(DS_ERR_ARG, "ds_reset_random: bad lattice shape");
+    if ((long long)d0 * d1 < h->n)
+        return fail(DS_ERR_ARG, "ds_reset_random: sample larger than population");   // as random.sample
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    ds::ResetArgs a;
+    a.E = h->E; a.n = h->n; a.d0 = d0; a.d1 = d1; a.real_bytes = h->real_bytes;
+    a.seed_lo = (unsigned)seed; a.seed_hi = (unsigned)(seed >> 32); a.stream = stream;
+    a.pitch = pitch;
+    a.pos = io->pos; a.vel = io->vel; a.t = io->t; a.fin = io->finished;
+    int threads = (int)(49152 / (sizeof(int) * (size_t)h->n));
+    threads = threads > 128 ? 128 : (threads < 1 ? 1 : threads);
+    const int blocks = (h->E + threads - 1) / threads;
+    const size_t smem = sizeof(int) * (size_t)h->n * threads;
+    if (h->real_bytes == 8) ds::reset_random_kernel<double><<<blocks, threads, smem, st>>>(a);
+    else ds::reset_random_kernel<float><<<blocks, threads, smem, st>>>(a);
+    DS_CUDA(cudaGetLastError());
+    return ds_observe(h, p, io, cuda_stream);
+}
+
 int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,
                  const ds_host_step_out *out, void *cuda_stream)
 {

@@ -1586,6 +1586,72 @@ __global__ void __launch_bounds__(256) returns_kernel(const ReturnsArgs a)
     }
 }
 
+// ---------------------------------------------------------------- device-side reset
+// SURVEY.md section 8f row 4 -- init_agents' random start (drone_env.py:193-205): n DISTINCT nodes of
+// the lattice {(idx * pitch, jdx * pitch)}, idx-major, drawn uniformly in order (random.sample).
+// Python's Mersenne stream cannot be reproduced here, so this path is stream-independent by
+// design: Philox4x32-10 keyed by (seed), counter (environment, draw block, stream id); every draw
+// is an unbiased index (Lemire's multiply-shift with rejection), duplicates within an environment
+// are redrawn -- which is exactly the distribution of random.sample.  One thread per environment;
+// its picks sit in shared memory for the duplicate test.  oracle/np_oracle.py restates the sampler
+// bit for bit (tests/test_gpu_parity.py::test_device_reset_*).
+struct ResetArgs {
+    int E, n, d0, d1, real_bytes;
+    unsigned seed_lo, seed_hi, stream;
+    double pitch;
+    void *pos, *vel;
+    int *t;
+    uint8_t *fin;
+};
+
+DS_HD void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4])
+{
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1;
+        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) reset_random_kernel(const ResetArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *picks = reinterpret_cast<int *>(smem_raw) + (size_t)threadIdx.x * a.n;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.E) return;
+    const unsigned L = (unsigned)a.d0 * (unsigned)a.d1;
+    const unsigned thresh = (0u - L) % L;                  // draws whose low product word is below are biased
+    unsigned rnd[4];
+    unsigned block = 0;
+    int have = 0;
+    using V2 = typename vec2_of<Real>::type;
+    V2 *pos = reinterpret_cast<V2 *>(a.pos) + (size_t)e * a.n;
+    V2 *vel = reinterpret_cast<V2 *>(a.vel) + (size_t)e * a.n;
+    for (int i = 0; i < a.n;) {
+        if (have == 0) { philox4x32_10((unsigned)e, block++, a.stream, 0u, a.seed_lo, a.seed_hi, rnd); have = 4; }
+        const unsigned long long m = (unsigned long long)rnd[4 - have] * L;
+        --have;
+        if ((unsigned)m < thresh) continue;                // Lemire: reject for exact uniformity
+        const int node = (int)(m >> 32);
+        bool dup = false;
+        for (int q = 0; q < i; ++q) dup |= (picks[q] == node);
+        if (dup) continue;                                 // without replacement
+        picks[i] = node;
+        V2 pv, zv;
+        pv.x = (Real)mul_rn((double)(node / a.d1), a.pitch);           // [idx * delta_l, jdx * delta_l] (:199)
+        pv.y = (Real)mul_rn((double)(node % a.d1), a.pitch);
+        zv.x = 0; zv.y = 0;
+        pos[i] = pv; vel[i] = zv;
+        ++i;
+    }
+    if (a.t) a.t[e] = 0;
+    if (a.fin) a.fin[e] = 0;
+}
+
 // Deterministic sum over environments of agg[E][4] -> out[0..3]; out[4] = E.
 __global__ void __launch_bounds__(1024) reduce_agg_kernel(const double *__restrict__ agg, int E,
                                                           double *__restrict__ out)

@@ -522,6 +522,61 @@ def test_controllers_vs_oracle_dense_batch():
         env.step_control("pid")
 
 
+@pytest.mark.parametrize("n,E,grid", [(10, 64, [5, 5]), (33, 20, [32, 32]), (128, 5, [64, 64]), (300, 3, [128, 128])])
+def test_device_reset_matches_restatement(n, E, grid):
+    """ds_reset_random against oracle/np_oracle.reset_random (same Philox counters, same unbiased
+    index, same redraw rule): start positions bit-exact; zero velocity, t = 0; the observation of
+    the start state is the one ds_observe / the oracle computes."""
+    from oracle import np_oracle
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    env = BatchedDrones(E, n, grid, "O", 2, np.ones(n), True, seed=0, warn=False)
+    env.step(torch.zeros((E, n, 2), dtype=torch.float64, device=env.device) + 0.3)      # dirty the state
+    env.reset_random(seed=0x1234567890ABCDEF, stream=5)
+    torch.cuda.synchronize()
+    d0, d1 = formation.lattice_shape(grid)
+    want = np_oracle.reset_random(E, n, d0, d1, formation.LATTICE_PITCH, 0x1234567890ABCDEF, 5)
+    assert np.array_equal(env.pos.cpu().numpy(), want)
+    assert not env.vel.any() and not env.internal_t.any() and not env.finished.any() and not env.done.any()
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, 2, True,
+                             c_oracle.default_params(env.collision_weight))
+    orc.set_state(want)
+    ref = orc.observe()
+    assert_close(env.rewards.cpu().numpy(), ref.r, FP64_TOL, "reward of the start state")
+    compare_obs(env.z_states.cpu().numpy(), env.Ni.cpu().numpy(), ref.z, ref.Ni, ref.tie, FP64_TOL, "start obs")
+
+
+def test_device_reset_statistics():
+    """The distribution random.sample gives (drone_env.py:204): every ordered pick is uniform over
+    the lattice and the picks of an environment are distinct -- chi-square over 2^17 environments;
+    streams are independent of each other and reproducible."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    n, E, grid = 5, 1 << 17, [5, 5]
+    env = BatchedDrones(E, n, grid, "O", 2, np.ones(n), True, seed=0, warn=False)
+    d0, d1 = formation.lattice_shape(grid)
+    L = d0 * d1
+    env.reset_random(seed=11, stream=0)
+    p0 = env.pos.clone()
+    nodes = np.rint(p0.cpu().numpy() / formation.LATTICE_PITCH).astype(np.int64)
+    flat = nodes[..., 0] * d1 + nodes[..., 1]
+    assert flat.min() >= 0 and flat.max() < L
+    srt = np.sort(flat, axis=1)
+    assert (srt[:, 1:] != srt[:, :-1]).all()                                   # distinct within an environment
+    assert int(env.n_collisions.sum()) == 0                                    # pitch 0.22 > 2 radii: no initial overlap
+    for col in range(n):                                                        # each ordered pick uniform
+        cnt = np.bincount(flat[:, col], minlength=L)
+        chi2 = ((cnt - E / L) ** 2 / (E / L)).sum()
+        assert chi2 < L + 6 * np.sqrt(2 * L), (col, chi2)                       # ~6 sigma of chi2(L-1)
+    # first two picks jointly: P(second == first + 1) = 1/L * (L-1)/(L-1)... simple independence proxy
+    same_row = (flat[:, 0] // d1 == flat[:, 1] // d1).mean()
+    assert abs(same_row - (d1 - 1) / (L - 1)) < 5 * np.sqrt(0.05 / E) + 2e-3
+    env.reset_random(seed=11, stream=0)
+    assert torch.equal(env.pos, p0)                                            # reproducible
+    env.reset_random(seed=11, stream=1)
+    assert (env.pos != p0).any(dim=-1).float().mean() > 0.9                    # a new stream moves (almost) everyone
+    env.reset_random(seed=12, stream=0)
+    assert (env.pos != p0).any(dim=-1).float().mean() > 0.9
+
+
 def test_error_behaviour():
     from scalable_collision_avoidance_rl_b200 import BatchedDrones, DroneStepError
     with pytest.raises(DroneStepError):

@@ -175,3 +175,24 @@ def test_control_oracles_match_reference(name, key, mode):
     for mod in (c_oracle, np_oracle):
         act = mod.control(mode, g["state_in"][:, :, 0:2], g["end_points"], g["d_safety"], None, u_max)
         assert np.array_equal(act, g[key], equal_nan=True), mod.__name__
+
+
+def test_philox_known_answers_and_reset_restatement():
+    """Philox4x32-10 of the device-reset restatement against the Random123 known-answer vectors;
+    the sampler returns distinct nodes of the reference's lattice (drone_env.py:193-205)."""
+    from oracle import np_oracle
+    from scalable_collision_avoidance_rl_b200 import formation
+    kat = [((0, 0, 0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 6, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for args, want in kat:
+        assert tuple(np_oracle._philox4x32_10(*args)) == want
+    d0, d1 = formation.lattice_shape([5, 5])
+    pos = np_oracle.reset_random(200, 10, d0, d1, formation.LATTICE_PITCH, seed=7, stream=3)
+    nodes = np.rint(pos / formation.LATTICE_PITCH).astype(int)
+    assert np.array_equal(pos, nodes * formation.LATTICE_PITCH)               # exactly idx * pitch
+    assert nodes.min() >= 0 and nodes[..., 0].max() < d0 and nodes[..., 1].max() < d1
+    flat = nodes[..., 0] * d1 + nodes[..., 1]
+    assert all(len(set(row)) == 10 for row in flat)
+    assert not np.array_equal(pos, np_oracle.reset_random(200, 10, d0, d1, formation.LATTICE_PITCH, 7, 4))
