@@ -651,10 +651,9 @@ int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, in
     a.seed_lo = (unsigned)seed; a.seed_hi = (unsigned)(seed >> 32); a.stream = stream;
     a.pitch = pitch;
     a.pos = io->pos; a.vel = io->vel; a.t = io->t; a.fin = io->finished;
-    int threads = (int)(49152 / (sizeof(int) * (size_t)h->n));
-    threads = threads > 128 ? 128 : (threads < 1 ? 1 : threads);
-    const int blocks = (h->E + threads - 1) / threads;
-    const size_t smem = sizeof(int) * (size_t)h->n * threads;
+    const int threads = 128, warps = threads / 32;         // one warp per environment
+    const int blocks = (h->E + warps - 1) / warps;
+    const size_t smem = sizeof(int) * (size_t)h->n * warps;
     if (h->real_bytes == 8) ds::reset_random_kernel<double><<<blocks, threads, smem, st>>>(a);
     else ds::reset_random_kernel<float><<<blocks, threads, smem, st>>>(a);
     DS_CUDA(cudaGetLastError());

@@ -1355,7 +1355,10 @@ rollout_kernel(const RolloutArgs ra)
         // (d) pass 2: one near pair per thread per round
         if (!inl) {
             const int M = (*sm.lcount < L) ? *sm.lcount : L;
-            for (int q = tid; q < M; q += blockDim.x) {
+            // the warp(s) of the agent threads integrate the next chunk in this phase: when the CTA
+            // has other warps, the pairs go to those
+            const int w0 = (more && A <= 32 && blockDim.x > 64) ? 32 : 0;
+            for (int q = tid - w0; q < M && tid >= w0; q += blockDim.x - w0) {
                 const unsigned w = sm.ent[q];
                 if (w == kEntSkip) continue;
                 const int row = (int)(w & 1023u), j = (int)((w >> 10) & 1023u), ri = (int)(w >> 20);
@@ -1592,8 +1595,8 @@ __global__ void __launch_bounds__(256) returns_kernel(const ReturnsArgs a)
 // Python's Mersenne stream cannot be reproduced here, so this path is stream-independent by
 // design: Philox4x32-10 keyed by (seed), counter (environment, draw block, stream id); every draw
 // is an unbiased index (Lemire's multiply-shift with rejection), duplicates within an environment
-// are redrawn -- which is exactly the distribution of random.sample.  One thread per environment;
-// its picks sit in shared memory for the duplicate test.  oracle/np_oracle.py restates the sampler
+// are redrawn -- which is exactly the distribution of random.sample.  One warp per environment;
+// its picks sit in shared memory for the (lane-parallel) duplicate test.  oracle/np_oracle.py restates the sampler
 // bit for bit (tests/test_gpu_parity.py::test_device_reset_*).
 struct ResetArgs {
     int E, n, d0, d1, real_bytes;
@@ -1619,10 +1622,13 @@ DS_HD void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, uns
 template <typename Real>
 __global__ void __launch_bounds__(128) reset_random_kernel(const ResetArgs a)
 {
+    // one WARP per environment: the draws are sequential (the accepted sequence is what defines the
+    // result), the duplicate test against the earlier picks is spread over the lanes
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *picks = reinterpret_cast<int *>(smem_raw) + (size_t)threadIdx.x * a.n;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.E) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int *picks = reinterpret_cast<int *>(smem_raw) + (size_t)w * a.n;
+    const int e = blockIdx.x * (blockDim.x >> 5) + w;
+    if (e >= a.E) return;                                  // whole warps leave together
     const unsigned L = (unsigned)a.d0 * (unsigned)a.d1;
     const unsigned thresh = (0u - L) % L;                  // draws whose low product word is below are biased
     unsigned rnd[4];
@@ -1638,18 +1644,23 @@ __global__ void __launch_bounds__(128) reset_random_kernel(const ResetArgs a)
         if ((unsigned)m < thresh) continue;                // Lemire: reject for exact uniformity
         const int node = (int)(m >> 32);
         bool dup = false;
-        for (int q = 0; q < i; ++q) dup |= (picks[q] == node);
-        if (dup) continue;                                 // without replacement
-        picks[i] = node;
-        V2 pv, zv;
-        pv.x = (Real)mul_rn((double)(node / a.d1), a.pitch);           // [idx * delta_l, jdx * delta_l] (:199)
-        pv.y = (Real)mul_rn((double)(node % a.d1), a.pitch);
-        zv.x = 0; zv.y = 0;
-        pos[i] = pv; vel[i] = zv;
+        for (int q = lane; q < i; q += 32) dup |= (picks[q] == node);
+        if (__any_sync(0xffffffffu, dup)) continue;        // without replacement
+        if (lane == 0) {
+            picks[i] = node;
+            V2 pv, zv;
+            pv.x = (Real)mul_rn((double)(node / a.d1), a.pitch);       // [idx * delta_l, jdx * delta_l] (:199)
+            pv.y = (Real)mul_rn((double)(node % a.d1), a.pitch);
+            zv.x = 0; zv.y = 0;
+            pos[i] = pv; vel[i] = zv;
+        }
+        __syncwarp();
         ++i;
     }
-    if (a.t) a.t[e] = 0;
-    if (a.fin) a.fin[e] = 0;
+    if (lane == 0) {
+        if (a.t) a.t[e] = 0;
+        if (a.fin) a.fin[e] = 0;
+    }
 }
 
 // Deterministic sum over environments of agg[E][4] -> out[0..3]; out[4] = E.
