@@ -27,9 +27,9 @@
 //           with a margin: the mask only has to be a superset of the live pairs;
 //   pass 2  only the NEAR pairs take the exact path: sqrt, clip, zero rule,
 //           division, log, collision test, k-nearest insert.
-// In the rollout kernel the near pairs of all rows of the CTA are compacted into a
-// shared-memory work list (row-contiguous, ascending j) and evaluated by ALL
-// threads of the CTA, one pair per thread per round, so that the expensive part
+// In the rollout kernel the near pairs of the rows of a warp are compacted into a
+// shared-memory work list (row-contiguous, ascending j) and evaluated by all
+// lanes of the warp, one pair per lane per round, so that the expensive part
 // (sqrt / div / log) is load balanced instead of paying for the row with the most
 // neighbours in every warp; each row then folds its own segment of results in
 // ascending j, the summation order of the reference (drone_env.py:282-283).
@@ -284,7 +284,7 @@ struct RolloutArgs {
     StepArgs s;
     int T, TC, n_actions;
     int L;                   // capacity of the CTA's near-pair work list
-    int inline_rows;         // n <= 32 only: rows evaluate their own near pairs (no work list)
+    int inline_rows;         // near pairs: 0 one CTA-wide work list, 1 rows evaluate their own (n <= 32), 2 warp-local lists
     const void *actions;     // Real [T][E][n][2] or null
     const uint8_t *aidx;     // u8 [T][E][n]
     const void *atable;      // Real [n_actions][2]
@@ -1150,16 +1150,20 @@ DS_HD int executed_slices(unsigned ngbits, int tt, int nsl, int max_steps, bool 
 // bit-exact single-integrator steps (A = I, B = dt I, drone_env.py:78-79,235) continuing from the
 // LAST slice of chunk c.  That is speculative only in appearance: if the episode ends inside
 // chunk c the environment stops stepping and the positions are never looked at.
-// One chunk, four barriers:
-//   (c) every row: pass 1 over its frame -> near masks; a warp scan + one smem atomic per warp
-//       gives the row a contiguous segment of the work list; entries written; the prefetched
-//       actions of chunk c + 1 -> act[]                                               | barrier
-//   (d) all threads: one near pair per thread per round (eval_pair); threads < A integrate
-//       chunk c + 1                                                                   | barrier
+// One chunk (default: warp-local work lists, TWO barriers):
+//   (c) every row: packed-f32 pass 1 over its frame -> near mask; a warp scan gives the row a
+//       contiguous segment of its WARP's slice of the work list; entries written; the action
+//       stream of chunk c + 2 starts its cp.async                                      | __syncwarp
+//   (d) the warp's lanes: one near pair per lane per round (eval_pair)                 | __syncwarp
 //   (e) every row folds its segment and finishes the row; collision count and not-at-goal bit
-//       posted to its frame / environment                                             | barrier
+//       posted to its frame / environment                                              | barrier
 //   (g) every row of an executed slice stores its outputs and adds to its running episode sums;
-//       one thread per environment advances t / alive                                 | barrier
+//       one thread per environment advances t / alive; one thread per agent integrates chunk
+//       c + 1                                                                          | barrier
+// ra.inline_rows selects the alternatives kept for comparison: 0 = one CTA-wide list (one shared
+// atomic per warp, barriers around (d), the next chunk integrated during (d) by a warp that takes
+// no pairs; -1...-2 %), 1 = rows evaluate their own near pairs (n <= 32; same instruction count at
+// config-3 density, worse when the rows of a warp differ more).
 // Register cap of the 256-thread instantiations.  The kernel is latency bound, so resident warps
 // matter, but a cap that makes ptxas spill costs more than it gains: measured on B200 (config 3,
 // 160-thread CTAs) 96 registers / 4 CTAs per SM = 1.30e10 agent-steps/s, 104-112 / 3 CTAs = 1.16e10,
@@ -1262,7 +1266,10 @@ rollout_kernel(const RolloutArgs ra)
     __syncthreads();
 
     // dense small-n frames: every row evaluates its own near pairs, two barriers per chunk
-    const bool inl = (NB == 1) && ra.inline_rows != 0;
+    const bool inl = (NB == 1) && ra.inline_rows == 1;
+    // warp-local work lists: list build, pair evaluation and fold of a warp's rows need no CTA barrier
+    const bool wl = ra.inline_rows == 2;
+    const int LW = L / (int)(blockDim.x >> 5);
     int ab = 0, ab1 = 1, ab2 = 2;                           // action buffers of chunk c, c + 1, c + 2
     for (int t0 = 0, buf = 0; t0 < T; t0 += TC, buf ^= 1) {
         const int nsl = (T - t0 < TC) ? (T - t0) : TC;      // slices in this chunk
@@ -1305,8 +1312,8 @@ rollout_kernel(const RolloutArgs ra)
                 }
             }
         }
-        // segment of the work list: exclusive scan over the warp, one atomic per warp
-        int seg = 0;
+        // segment of the work list: exclusive scan over the warp
+        int seg = 0, wbase = 0, wtotal = 0;
         bool listed = true;
         if (!inl) {
             int incl = ncnt;
@@ -1315,11 +1322,18 @@ rollout_kernel(const RolloutArgs ra)
                 const int v = __shfl_up_sync(0xffffffffu, incl, w);
                 if (lane >= w) incl += v;
             }
-            int wbase = 0;
-            if (lane == 31 && incl > 0) wbase = atomicAdd(sm.lcount, incl);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            int lend;                                        // end of the list region this row may use
+            if (wl) {                                        // warp-local list: a fixed slice per warp
+                wbase = (tid >> 5) * LW;
+                lend = wbase + LW;
+                wtotal = __shfl_sync(0xffffffffu, incl, 31);
+            } else {                                         // CTA-wide list: one atomic per warp
+                if (lane == 31 && incl > 0) wbase = atomicAdd(sm.lcount, incl);
+                wbase = __shfl_sync(0xffffffffu, wbase, 31);
+                lend = L;
+            }
             seg = wbase + incl - ncnt;
-            listed = ncnt == 0 || seg + ncnt <= L;           // otherwise the row evaluates itself in (e)
+            listed = ncnt == 0 || seg + ncnt <= lend;        // otherwise the row evaluates itself in (e)
             if (valid && ncnt > 0) {
                 unsigned *ep = sm.ent + seg;
                 if (listed) {
@@ -1335,7 +1349,7 @@ rollout_kernel(const RolloutArgs ra)
                         }
                     }
                 } else {
-                    for (int q = seg; q < L && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
+                    for (int q = seg; q < lend && q < seg + ncnt; ++q) sm.ent[q] = kEntSkip;
                 }
             }
         }
@@ -1351,14 +1365,16 @@ rollout_kernel(const RolloutArgs ra)
         }
         cp_async_commit();
         cp_async_wait_but_one();
-        if (!inl) __syncthreads();
+        if (wl) __syncwarp(); else if (!inl) __syncthreads();
         // (d) pass 2: one near pair per thread per round
         if (!inl) {
-            const int M = (*sm.lcount < L) ? *sm.lcount : L;
-            // the warp(s) of the agent threads integrate the next chunk in this phase: when the CTA
-            // has other warps, the pairs go to those
-            const int w0 = (more && A <= 32 && blockDim.x > 64) ? 32 : 0;
-            for (int q = tid - w0; q < M && tid >= w0; q += blockDim.x - w0) {
+            // CTA-wide list: the warp(s) of the agent threads integrate the next chunk in this phase,
+            // so when the CTA has other warps the pairs go to those.  Warp-local list: every warp
+            // works through its own slice.
+            const int w0 = (!wl && more && A <= 32 && blockDim.x > 64) ? 32 : 0;
+            const int M = wl ? ((wtotal < LW) ? wtotal : LW) : ((*sm.lcount < L) ? *sm.lcount : L);
+            const int q0 = wl ? wbase + lane : tid - w0, qe = wl ? wbase + M : M, qs = wl ? 32 : (int)blockDim.x - w0;
+            for (int q = q0; q < qe && tid >= w0; q += qs) {
                 const unsigned w = sm.ent[q];
                 if (w == kEntSkip) continue;
                 const int row = (int)(w & 1023u), j = (int)((w >> 10) & 1023u), ri = (int)(w >> 20);
@@ -1371,7 +1387,9 @@ rollout_kernel(const RolloutArgs ra)
                 sm.ent[q] = pack_result(j, po.in_disk, po.coll, (po.in_disk ? 1 : 0) - ((ca.x <= cbj.y) ? 1 : 0) + 1);
             }
         }
-        if (!inl) {
+        if (wl) {
+            __syncwarp();
+        } else if (!inl) {
             if (agent_thread && more && env_alive)
                 integrate(sm.pos(buf)[(TC - 1) * A + tid], ab1, buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
             __syncthreads();
@@ -1401,8 +1419,8 @@ rollout_kernel(const RolloutArgs ra)
         }
         if (tid == 0) *sm.lcount = 0;                        // every thread has read it in (d)
         __syncthreads();
-        // inline mode: the next chunk's actions are staged by now; integrate here
-        if (inl && agent_thread && more && env_alive)
+        // two-barrier modes: the next chunk's actions are staged by now; integrate here
+        if ((inl || wl) && agent_thread && more && env_alive)
             integrate(sm.pos(buf)[(TC - 1) * A + tid], ab1, buf ^ 1, (T - t0 - TC < TC) ? (T - t0 - TC) : TC);
         // (g) stores
         int ne = 0;
