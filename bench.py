@@ -57,7 +57,8 @@ def peaks():
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout launch from the committed
 # `ncu --set full` captures (profiles/r01/*_summary.md), keyed by (workload, dtype): bytes per launch.
 NCU_TRAFFIC = {
-    ("config3", "f64"): 133.4e6 + 836.8e6,     # profiles/r01/final_prof_config3_summary.md
+    ("config3", "f64"): 133.5e6 + 836.9e6,     # profiles/r01/final_prof_config3_summary.md
+    ("hbm", "f64"): 3738.1e6 + 23873.4e6,      # profiles/r01/final_prof_hbm_summary.md
     ("config5", "f64"): 424.1e6 + 2788.5e6,    # profiles/r01/e_prof_config5_summary.md
 }
 
