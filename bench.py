@@ -381,7 +381,7 @@ def run_ours(args, wl):
                    "log_mode": args.log_mode},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
-                     "traffic": NCU_TRAFFIC.get((args.workload, args.dtype)) if T == EPISODE else None,
+                     "traffic": NCU_TRAFFIC.get((args.workload, args.dtype)) if T == wl.get("episode", EPISODE) else None,
                      "traffic_unit": "DRAM bytes per launch (ncu capture, profiles/r01)",
                      "algorithmic_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src,
                      "kernel": "ds::rollout_kernel", "bytes_per_agent_step": bpas,

@@ -490,6 +490,8 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_
     ra.s.G = h->ro_G;
     ra.TC = h->ro_TC; ra.n_actions = ro->n_actions; ra.L = h->ro_L;
     ra.inline_rows = h->ro_inline;
+    auto magic = [](unsigned d) -> unsigned { return d <= 1 ? 0u : (unsigned)((((unsigned long long)1 << 32) + d - 1) / d); };
+    ra.mulA = magic((unsigned)(h->ro_G * h->n)); ra.mulN = magic((unsigned)h->n);
     ra.atable = ro->action_table;
     ra.agg = ro->agg; ra.done = ro->done;
     if (ro->T == 0) return DS_OK;

@@ -284,6 +284,7 @@ struct RolloutArgs {
     StepArgs s;
     int T, TC, n_actions;
     int L;                   // capacity of the CTA's near-pair work list
+    unsigned mulA, mulN;     // ceil(2^32 / (G n)), ceil(2^32 / n) (0 when the divisor is 1): tid -> (slice, env, agent)
     int inline_rows;         // near pairs: 0 one CTA-wide work list, 1 rows evaluate their own (n <= 32), 2 warp-local lists
     const void *actions;     // Real [T][E][n][2] or null
     const uint8_t *aidx;     // u8 [T][E][n]
@@ -1199,8 +1200,9 @@ rollout_kernel(const RolloutArgs ra)
     const int A = G * n;                              // agents per slice in this CTA
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int s = tid / A, ag = tid - s * A;          // time slice within the chunk, agent slot
-    const int le = ag / n, i = ag - le * n;
+    // (exact multiply-high division: ptxas re-derives these per chunk rather than keep them live)
+    const int s = ra.mulA ? (int)__umulhi((unsigned)tid, ra.mulA) : tid, ag = tid - s * A;   // slice in the chunk, agent slot
+    const int le = ra.mulN ? (int)__umulhi((unsigned)ag, ra.mulN) : ag, i = ag - le * n;
     const int e = blockIdx.x * G + le;
     const bool active = (s < TC) && (e < E);
     const unsigned g = active ? (unsigned)e * n + i : 0u;
