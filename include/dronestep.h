@@ -202,6 +202,37 @@ int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p,
 int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, int32_t d1, double pitch,
                     const ds_params *p, const ds_buffers *io, void *cuda_stream);
 
+/* Batched policy inference (SAC_agents.py:60-82,170-180: `actions = agents.forward(z_states, Ni)`):
+ * the reference's per-agent actors DiscreteSoftmaxNN (utils.py:255-318), in_dim -> 300 -> 300 ->
+ * n_actions with ReLU / ReLU / softmax, evaluated for all E x n (environment, agent) pairs on the
+ * tensor cores (tcgen05, 3xTF32: fp32 parity), one network per agent.  ds_policy_create packs the
+ * host fp32 weights (row-major as torch stores nn.Linear.weight) into the device operand layout. */
+typedef struct ds_policy ds_policy;
+typedef struct ds_policy_config {
+    int32_t n_agents;        /* number of networks */
+    int32_t in_dim;          /* (k+1) * cols of the observation, <= 16 */
+    int32_t n_actions;       /* <= 16 */
+    int32_t real_bytes;      /* precision of the action table / actions: 4 or 8 */
+    int32_t device;
+    int32_t _pad;
+    const float *W1, *b1;    /* [n][300][in_dim], [n][300]   input_layer   (utils.py:276) */
+    const float *W2, *b2;    /* [n][300][300],   [n][300]    hidden_layer1 (utils.py:279) */
+    const float *W3, *b3;    /* [n][A][300],     [n][A]      out_1         (utils.py:282) */
+    const double *action_table; /* [A][2] action_list (utils.py:262-269) */
+} ds_policy_config;
+int ds_policy_create(const ds_policy_config *cfg, ds_policy **out);
+void ds_policy_destroy(ds_policy *pol);
+typedef struct ds_policy_io {
+    const void *z;           /* Real [E][n][in_dim] observations (device), e.g. ds_buffers.z */
+    void *actions;           /* out Real [E][n][2]: action_list[index] */
+    uint8_t *action_idx;     /* out u8 [E][n] (may be NULL) */
+    float *probs;            /* out f32 [E][n][A] (may be NULL) */
+    uint64_t seed;           /* sampling: Philox4x32-10(seed; environment, agent, stream) */
+    uint32_t stream;
+    uint32_t _pad;
+} ds_policy_io;
+int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void *cuda_stream);
+
 /* One step with HOST action / result buffers holding Real of the handle's
  * precision (pinned memory recommended): H2D actions -> ds_step -> D2H of the
  * reference's 6-tuple (drone_env.py:258), then one stream synchronise.  Output

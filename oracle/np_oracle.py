@@ -196,3 +196,38 @@ def reset_random(n_envs, n_agents, d0, d1, pitch, seed, stream):
         out[e, :, 0] = (nodes // d1) * pitch
         out[e, :, 1] = (nodes % d1) * pitch
     return out
+
+
+def policy_probs(z, W1, b1, W2, b2, W3, b3):
+    """fp32 restatement of DiscreteSoftmaxNN.forward (reference utils.py:287-302) for a batch:
+    z [B, in] -> softmax(W3 relu(W2 relu(W1 z + b1) + b2) + b3) [B, A].  The reference evaluates one
+    observation at a time with softmax over dim 0 of the action vector (utils.py:283)."""
+    f = np.float32
+    x = np.asarray(z, np.float64).astype(f)                              # torch.tensor(z, dtype=float32) (:305)
+    l1 = np.maximum(x @ np.asarray(W1, f).T + np.asarray(b1, f), f(0))
+    l2 = np.maximum(l1 @ np.asarray(W2, f).T + np.asarray(b2, f), f(0))
+    o = l2 @ np.asarray(W3, f).T + np.asarray(b3, f)
+    o = o - o.max(axis=1, keepdims=True)
+    e = np.exp(o)
+    return (e / e.sum(axis=1, keepdims=True)).astype(f)
+
+
+def policy_sample(probs, n_envs, n_agents, seed, stream):
+    """Action index drawn by the device policy (policy_kernel): u = top 24 bits of Philox4x32-10
+    keyed by the seed at counter (environment, agent, stream, 1), first index whose running fp32
+    sum of probabilities exceeds u (the last index if none does)."""
+    probs = np.asarray(probs, np.float32).reshape(n_envs, n_agents, -1)
+    idx = np.zeros((n_envs, n_agents), np.uint8)
+    for e in range(n_envs):
+        for i in range(n_agents):
+            r = _philox4x32_10(e, i, stream, 1, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)[0]
+            u = np.float32(r >> 8) * np.float32(2.0 ** -24)
+            c = np.float32(0)
+            pick = probs.shape[-1] - 1
+            for a in range(probs.shape[-1]):
+                c = np.float32(c + probs[e, i, a])
+                if u < c:
+                    pick = a
+                    break
+            idx[e, i] = pick
+    return idx

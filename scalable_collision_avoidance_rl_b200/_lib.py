@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "ds_default_params", "ds_step", "ds_observe", "ds_rollout", "ds_reduce_aggregates",
     "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_rollout_host", "ds_returns",
     "ds_step_control", "ds_rollout_control", "ds_reset_random",
+    "ds_policy_create", "ds_policy_destroy", "ds_policy_forward",
 )
 
 
@@ -63,6 +64,17 @@ class ds_returns_io(ctypes.Structure):
                 ("returns", c_void_p), ("advantage", c_void_p), ("count", c_void_p)]
 
 
+class ds_policy_config(ctypes.Structure):
+    _fields_ = [("n_agents", c_int32), ("in_dim", c_int32), ("n_actions", c_int32), ("real_bytes", c_int32),
+                ("device", c_int32), ("_pad", c_int32), ("W1", c_void_p), ("b1", c_void_p), ("W2", c_void_p),
+                ("b2", c_void_p), ("W3", c_void_p), ("b3", c_void_p), ("action_table", c_void_p)]
+
+
+class ds_policy_io(ctypes.Structure):
+    _fields_ = [("z", c_void_p), ("actions", c_void_p), ("action_idx", c_void_p), ("probs", c_void_p),
+                ("seed", ctypes.c_uint64), ("stream", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
+
+
 class ds_host_step_out(ctypes.Structure):
     _fields_ = [("pos", c_void_p), ("vel", c_void_p), ("z", c_void_p), ("reward", c_void_p),
                 ("true_reward", c_void_p), ("Ni", c_void_p), ("ncoll", c_void_p),
@@ -99,9 +111,10 @@ def load():
     lib.ds_last_error.restype = ctypes.c_char_p
     lib.ds_destroy.restype = None
     lib.ds_default_params.restype = None
+    lib.ds_policy_destroy.restype = None
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)   # AttributeError if the ABI is incomplete
-        if name not in ("ds_last_error", "ds_destroy", "ds_default_params"):
+        if name not in ("ds_last_error", "ds_destroy", "ds_default_params", "ds_policy_destroy"):
             fn.restype = ctypes.c_int
     _lib = lib
     return lib

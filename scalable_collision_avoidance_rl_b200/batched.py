@@ -108,6 +108,9 @@ class BatchedDrones:
         h = getattr(self, "_h", None)
         if h is not None and h.value:
             try:
+                pol = getattr(self, "_pol", None)
+                if pol is not None and pol.value:
+                    self.lib.ds_policy_destroy(pol)
                 self.lib.ds_destroy(h)
             except Exception:
                 pass
@@ -412,6 +415,44 @@ class BatchedDrones:
         io.count = buf("count", torch.uint8).data_ptr()
         _lib.check(self.lib.ds_returns(self._h, ctypes.byref(io), self._stream()), "ds_returns")
         return out
+
+    # ------------------------------------------------------------------ policy
+    def load_policy(self, W1, b1, W2, b2, W3, b3, action_table):
+        """Per-agent actors of the reference (utils.DiscreteSoftmaxNN: in -> 300 -> 300 -> A) for
+        policy_forward(): fp32 arrays stacked over agents, W* as torch stores nn.Linear.weight
+        ([n,300,in], [n,300,300], [n,A,300]); action_table [A,2] = action_list (ds_policy_create)."""
+        f = lambda x: np.ascontiguousarray(np.asarray(x, np.float32))
+        W1, b1, W2, b2, W3, b3 = map(f, (W1, b1, W2, b2, W3, b3))
+        n, A = self.n_agents, W3.shape[1]
+        in_dim = W1.shape[2]
+        assert W1.shape == (n, 300, in_dim) and W2.shape == (n, 300, 300) and W3.shape == (n, A, 300)
+        assert b1.shape == (n, 300) and b2.shape == (n, 300) and b3.shape == (n, A)
+        tab = np.ascontiguousarray(np.asarray(action_table, np.float64).reshape(A, 2))
+        cfg = _lib.ds_policy_config(n, in_dim, A, _REAL[self.dtype], self.device.index or 0, 0,
+                                    W1.ctypes.data, b1.ctypes.data, W2.ctypes.data, b2.ctypes.data,
+                                    W3.ctypes.data, b3.ctypes.data, tab.ctypes.data)
+        old = getattr(self, "_pol", None)
+        if old is not None and old.value:
+            self.lib.ds_policy_destroy(old)
+        self._pol = ctypes.c_void_p()
+        _lib.check(self.lib.ds_policy_create(ctypes.byref(cfg), ctypes.byref(self._pol)), "ds_policy_create")
+        self._pol_A = A
+        self.actions = torch.zeros((self.n_envs, n, 2), dtype=self.dtype, device=self.device)
+        self.action_idx = torch.zeros((self.n_envs, n), dtype=torch.uint8, device=self.device)
+        self.action_probs = torch.zeros((self.n_envs, n, A), dtype=torch.float32, device=self.device)
+
+    def policy_forward(self, seed=0, stream=0, z=None, want_probs=True):
+        """`actions = agents.forward(z_states, Ni)` (SAC_agents.py:170-180) for every environment on
+        the device (ds_policy_forward, tcgen05): probabilities of each agent's own network on its
+        observation, one action index drawn per (environment, agent) from Philox(seed; e, i, stream).
+        Returns (actions [E,n,2], action_idx [E,n], probs [E,n,A] or None); feed `actions` to step()."""
+        z = self.z_states if z is None else z
+        assert z.is_cuda and z.dtype == self.dtype and z.is_contiguous()
+        io = _lib.ds_policy_io(z.data_ptr(), self.actions.data_ptr(), self.action_idx.data_ptr(),
+                               self.action_probs.data_ptr() if want_probs else None, int(seed), int(stream), 0)
+        _lib.check(self.lib.ds_policy_forward(self._h, self._pol, ctypes.byref(io), self._stream()),
+                   "ds_policy_forward")
+        return self.actions, self.action_idx, (self.action_probs if want_probs else None)
 
     def episode_aggregates(self):
         """Device-side sum over this rank's environments of the per-env episode accumulators

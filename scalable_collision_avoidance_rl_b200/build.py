@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdronestep.so")
 SOURCES = [os.path.join(CSRC, "dronestep_abi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "dronestep_kernels.cuh"),
+DEPS = SOURCES + [os.path.join(CSRC, "dronestep_kernels.cuh"), os.path.join(CSRC, "dronestep_policy.cuh"),
                   os.path.join(os.path.dirname(PKG_DIR), "include", "dronestep.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]

@@ -6,6 +6,7 @@
 // CUDA device every compute entry fails with DS_ERR_NO_DEVICE.
 #include "../../include/dronestep.h"
 #include "dronestep_kernels.cuh"
+#include "dronestep_policy.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -663,6 +664,108 @@ int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, in
     else ds::reset_random_kernel<float><<<blocks, threads, smem, st>>>(a);
     DS_CUDA(cudaGetLastError());
     return ds_observe(h, p, io, cuda_stream);
+}
+
+struct ds_policy {
+    int n, in_dim, A, real_bytes, device;
+    float *W1 = nullptr, *b1 = nullptr, *W2p = nullptr, *b2 = nullptr, *W3 = nullptr, *b3 = nullptr;
+    void *atable = nullptr;
+};
+
+int ds_policy_create(const ds_policy_config *cfg, ds_policy **out)
+{
+    if (!cfg || !out) return fail(DS_ERR_ARG, "ds_policy_create: NULL argument");
+    *out = nullptr;
+    if (cfg->n_agents < 1 || cfg->in_dim < 1 || cfg->in_dim > ds::kPolMaxIn || cfg->n_actions < 1 ||
+        cfg->n_actions > ds::kPolMaxA || (cfg->real_bytes != 4 && cfg->real_bytes != 8))
+        return fail(DS_ERR_ARG, "ds_policy_create: need in_dim <= 16, n_actions <= 16, real_bytes 4 or 8");
+    if (!cfg->W1 || !cfg->b1 || !cfg->W2 || !cfg->b2 || !cfg->W3 || !cfg->b3 || !cfg->action_table)
+        return fail(DS_ERR_ARG, "ds_policy_create: weight arrays must be non-NULL");
+    const int ndev = ds_device_count();
+    if (ndev < 1) return fail(DS_ERR_NO_DEVICE, "ds_policy_create: no CUDA device visible; libdronestep has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(DS_ERR_ARG, "ds_policy_create: bad device ordinal");
+    DeviceGuard guard(cfg->device);
+    const int n = cfg->n_agents, H = ds::kPolHidden, NP = ds::kPolNP, KP = ds::kPolKP, A = cfg->n_actions;
+    // W2 -> [agent][chunk of 32 k][hi, lo][k-group of 4][304 rows][4]: the K-major core-matrix layout the
+    // kernel's shared-memory descriptors describe; hi = the 19 bits kind::tf32 reads, lo = the rest
+    std::vector<float> w2p((size_t)n * (KP / 32) * 2 * 8 * NP * 4, 0.f), b2p((size_t)n * NP, 0.f), w3p((size_t)n * A * NP, 0.f);
+    for (int i = 0; i < n; ++i) {
+        for (int r = 0; r < H; ++r) {
+            b2p[(size_t)i * NP + r] = cfg->b2[(size_t)i * H + r];
+            for (int k = 0; k < H; ++k) {
+                const float w = cfg->W2[((size_t)i * H + r) * H + k];
+                uint32_t bits; std::memcpy(&bits, &w, 4);
+                bits &= 0xffffe000u;
+                float hi; std::memcpy(&hi, &bits, 4);
+                const int kc = k / 32, kg = (k % 32) / 4, q = k % 4;
+                const size_t base = ((((size_t)i * (KP / 32) + kc) * 2) * 8 + kg) * NP;
+                w2p[(base + r) * 4 + q] = hi;
+                w2p[(base + (size_t)8 * NP + r) * 4 + q] = w - hi;
+            }
+        }
+        for (int aidx = 0; aidx < A; ++aidx)
+            for (int k = 0; k < H; ++k) w3p[((size_t)i * A + aidx) * NP + k] = cfg->W3[((size_t)i * A + aidx) * H + k];
+    }
+    ds_policy *p = new ds_policy();
+    p->n = n; p->in_dim = cfg->in_dim; p->A = A; p->real_bytes = cfg->real_bytes; p->device = cfg->device;
+    auto up = [](float **dst, const float *src, size_t count) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void **)dst, count * sizeof(float));
+        return e != cudaSuccess ? e : cudaMemcpy(*dst, src, count * sizeof(float), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = up(&p->W1, cfg->W1, (size_t)n * H * cfg->in_dim);
+    if (e == cudaSuccess) e = up(&p->b1, cfg->b1, (size_t)n * H);
+    if (e == cudaSuccess) e = up(&p->W2p, w2p.data(), w2p.size());
+    if (e == cudaSuccess) e = up(&p->b2, b2p.data(), b2p.size());
+    if (e == cudaSuccess) e = up(&p->W3, w3p.data(), w3p.size());
+    if (e == cudaSuccess) e = up(&p->b3, cfg->b3, (size_t)n * A);
+    if (e == cudaSuccess) e = cudaMalloc(&p->atable, (size_t)A * 2 * cfg->real_bytes);
+    if (e == cudaSuccess) {
+        if (cfg->real_bytes == 8) e = cudaMemcpy(p->atable, cfg->action_table, (size_t)A * 16, cudaMemcpyHostToDevice);
+        else {
+            std::vector<float> t((size_t)A * 2);
+            for (int q = 0; q < 2 * A; ++q) t[q] = (float)cfg->action_table[q];
+            e = cudaMemcpy(p->atable, t.data(), (size_t)A * 8, cudaMemcpyHostToDevice);
+        }
+    }
+    if (e != cudaSuccess) { ds_policy_destroy(p); return fail(DS_ERR_CUDA, std::string("ds_policy_create: ") + cudaGetErrorString(e)); }
+    *out = p;
+    return DS_OK;
+}
+
+void ds_policy_destroy(ds_policy *p)
+{
+    if (!p) return;
+    DeviceGuard guard(p->device);
+    cudaFree(p->W1); cudaFree(p->b1); cudaFree(p->W2p); cudaFree(p->b2); cudaFree(p->W3); cudaFree(p->b3); cudaFree(p->atable);
+    delete p;
+}
+
+int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void *cuda_stream)
+{
+    if (!h || !pol || !io || !io->z || !io->actions) return fail(DS_ERR_ARG, "ds_policy_forward: NULL argument");
+    if (pol->n != h->n) return fail(DS_ERR_ARG, "ds_policy_forward: the policy has a different number of agents");
+    if (pol->real_bytes != h->real_bytes || pol->device != h->device)
+        return fail(DS_ERR_ARG, "ds_policy_forward: the policy was created for another precision / device");
+    if (pol->in_dim != (h->k + 1) * (h->simplify ? 2 : 5))
+        return fail(DS_ERR_ARG, "ds_policy_forward: in_dim != (k + 1) * cols of the observation");
+    DeviceGuard guard(h->device);
+    ds::PolicyArgs a;
+    a.E = h->E; a.n = h->n; a.in_dim = pol->in_dim; a.n_actions = pol->A; a.real_bytes = h->real_bytes;
+    a.seed_lo = (unsigned)io->seed; a.seed_hi = (unsigned)(io->seed >> 32); a.stream = io->stream;
+    a.z = io->z; a.W1 = pol->W1; a.b1 = pol->b1; a.W2p = pol->W2p; a.b2 = pol->b2; a.W3 = pol->W3; a.b3 = pol->b3;
+    a.atable = pol->atable; a.act = io->actions; a.aidx = io->action_idx; a.probs = io->probs;
+    const dim3 grid((h->E + 127) / 128, h->n);
+    const size_t smem = sizeof(ds::PolicySmem) + 128;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (h->real_bytes == 8) {
+        DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ds::policy_kernel<double><<<grid, 128, smem, st>>>(a);
+    } else {
+        DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ds::policy_kernel<float><<<grid, 128, smem, st>>>(a);
+    }
+    DS_CUDA(cudaGetLastError());
+    return DS_OK;
 }
 
 int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,

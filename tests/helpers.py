@@ -17,7 +17,7 @@ FP64_TOL = 1e-9
 def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                  if not p.endswith("ctor_table.npz") and not os.path.basename(p).startswith(("returns_", "control_")))
+                  if not p.endswith("ctor_table.npz") and not os.path.basename(p).startswith(("returns_", "control_", "policynet_")))
 
 
 def load_golden(name):

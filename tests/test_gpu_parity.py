@@ -577,6 +577,97 @@ def test_device_reset_statistics():
     assert (env.pos != p0).any(dim=-1).float().mean() > 0.9
 
 
+def _torch_like_weights(rng, n, in_dim, A):
+    u = lambda shape, fan: rng.uniform(-1, 1, shape).astype(np.float32) / np.float32(np.sqrt(fan))
+    return (u((n, 300, in_dim), in_dim), u((n, 300), in_dim), u((n, 300, 300), 300), u((n, 300), 300),
+            u((n, A, 300), 300), u((n, A), 300))
+
+
+def test_policy_forward_vs_reference_golden():
+    """ds_policy_forward (tcgen05, 3xTF32) with the reference's own pretrained actors
+    (softmax8_n5, agents 0 and 1) on observations of a recorded episode: probabilities within 1e-5
+    of what the reference's DiscreteSoftmaxNN.forward returned (fp32), sampled index = inverse CDF
+    of the Philox uniform on the device's own probabilities, action = action_list[index]."""
+    import os
+    from oracle import np_oracle
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "policynet_n5_agents01.npz"))
+    T, A = g["probs"].shape[0], int(g["n_actions"])
+    use = [0, 1, 0]                                        # three agents (k = 2 needs n >= 3): networks 0, 1, 0
+    n = len(use)
+    env = BatchedDrones(T, n, [5, 5], "O", 2, np.ones(n), True, seed=0, warn=False)
+    W = [np.stack([g[f"{w}_{a}"] for a in use]) for w in ("W1", "b1", "W2", "b2", "W3", "b3")]
+    env.load_policy(*W, g["action_list"])
+    z = torch.as_tensor(g["z"][:, use].reshape(T, n, 3, 2), device=env.device).contiguous()
+    act, idx, probs = env.policy_forward(seed=99, stream=7, z=z)
+    torch.cuda.synchronize()
+    probs = probs.cpu().numpy(); idx = idx.cpu().numpy()
+    assert np.abs(probs - g["probs"][:, use]).max() <= 1e-5
+    want = np.stack([np_oracle.policy_probs(g["z"][:, a], *[g[f"{w}_{a}"] for w in ("W1", "b1", "W2", "b2", "W3", "b3")])
+                     for a in use], 1)
+    assert np.abs(probs - want).max() <= 2e-6
+    assert np.array_equal(idx, np_oracle.policy_sample(probs, T, n, 99, 7))
+    assert np.array_equal(act.cpu().numpy(), g["action_list"][idx])
+
+
+@pytest.mark.parametrize("n,E,k,simplify,A", [(10, 1000, 2, True, 16), (5, 129, 2, False, 8), (32, 300, 1, True, 5)])
+def test_policy_forward_vs_fp32_restatement(n, E, k, simplify, A):
+    """Random torch-style weights (layers 2 and 3 scaled x3 to spread the logits), one network per
+    agent, E not a multiple of the 128-row tile: probabilities against the fp32 NumPy restatement
+    (3e-5: two fp32 summation orders over 300 terms on logits of magnitude ~10 differ by that much;
+    the unscaled reference networks are asserted at 1e-5 / 2e-6 above), index and action as
+    specified; the action then drives a step."""
+    from oracle import np_oracle
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    rng = np.random.default_rng(n * 7 + A)
+    grid = [5, 5] if n <= 10 else [32, 32]
+    env = BatchedDrones(E, n, grid, "O", k, np.ones(n), simplify, seed=2, warn=False)
+    in_dim = (k + 1) * (2 if simplify else 5)
+    W = _torch_like_weights(rng, n, in_dim, A)
+    W = tuple(w * np.float32(3) if j in (2, 4) else w for j, w in enumerate(W))       # spread the logits
+    tab = formation.unit_action_table(A)
+    env.load_policy(*W, tab)
+    act, idx, probs = env.policy_forward(seed=5, stream=1)                           # on the live observation
+    torch.cuda.synchronize()
+    z = env.z_states.cpu().numpy().reshape(E, n, in_dim)
+    probs = probs.cpu().numpy(); idx = idx.cpu().numpy()
+    for i in range(n):
+        want = np_oracle.policy_probs(z[:, i], *[w[i] for w in W])
+        assert np.abs(probs[:, i] - want).max() <= 3e-5, i
+    assert np.abs(probs.sum(-1) - 1).max() < 1e-5
+    assert np.array_equal(idx, np_oracle.policy_sample(probs, E, n, 5, 1))
+    assert np.array_equal(act.cpu().numpy(), tab[idx])
+    p0 = env.pos.clone()
+    env.step(act)
+    torch.cuda.synchronize()
+    assert np.array_equal(env.pos.cpu().numpy(), p0.cpu().numpy() + 0.05 * tab[idx])
+
+
+def test_policy_sampling_statistics():
+    """Same observation in 2^15 environments: the sampled indices follow the probabilities
+    (chi-square), different streams give different draws, same stream reproduces."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    n, E, A = 3, 1 << 15, 8
+    rng = np.random.default_rng(1)
+    env = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=0, warn=False)
+    env.load_policy(*_torch_like_weights(rng, n, 6, A), formation.unit_action_table(A))
+    z = torch.as_tensor(np.broadcast_to(rng.uniform(-2, 2, (1, n, 3, 2)), (E, n, 3, 2)).copy(), device=env.device)
+    _, idx, probs = env.policy_forward(seed=8, stream=0, z=z)
+    torch.cuda.synchronize()
+    idx0 = idx.clone()
+    p = probs[0].cpu().numpy().astype(np.float64)
+    for i in range(n):
+        cnt = np.bincount(idx[:, i].cpu().numpy(), minlength=A)
+        exp = p[i] * E
+        keep = exp > 5
+        chi2 = ((cnt[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+        assert chi2 < keep.sum() + 6 * np.sqrt(2 * keep.sum()) + 5, (i, chi2)
+    _, idx1, _ = env.policy_forward(seed=8, stream=0, z=z)
+    assert torch.equal(idx1, idx0)
+    _, idx2, _ = env.policy_forward(seed=8, stream=1, z=z)
+    assert (idx2 != idx0).float().mean() > 0.3
+
+
 def test_error_behaviour():
     from scalable_collision_avoidance_rl_b200 import BatchedDrones, DroneStepError
     with pytest.raises(DroneStepError):

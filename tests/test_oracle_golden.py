@@ -196,3 +196,17 @@ def test_philox_known_answers_and_reset_restatement():
     flat = nodes[..., 0] * d1 + nodes[..., 1]
     assert all(len(set(row)) == 10 for row in flat)
     assert not np.array_equal(pos, np_oracle.reset_random(200, 10, d0, d1, formation.LATTICE_PITCH, 7, 4))
+
+
+def test_policy_restatement_matches_reference():
+    """fp32 restatement of DiscreteSoftmaxNN.forward against the probabilities the reference's own
+    pretrained actors return (oracle/make_golden_policy.py): <= 5e-7; sampling restatement sane."""
+    import os
+    from oracle import np_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "policynet_n5_agents01.npz"))
+    for a in (0, 1):
+        p = np_oracle.policy_probs(g["z"][:, a], *[g[f"{w}_{a}"] for w in ("W1", "b1", "W2", "b2", "W3", "b3")])
+        assert np.abs(p - g["probs"][:, a]).max() <= 5e-7
+        assert np.abs(p.sum(1) - 1).max() < 1e-6
+    idx = np_oracle.policy_sample(g["probs"][:, :1], g["probs"].shape[0], 1, seed=3, stream=0)
+    assert idx.shape == (g["probs"].shape[0], 1) and idx.max() < int(g["n_actions"])
