@@ -8,7 +8,8 @@
 //   it once per agent per step on the host (SAC_agents.py:60-82,170-180).
 // Batched over E environments the 300 x 300 layer is a grouped GEMM -- n groups (one network per
 // agent), M = E rows each -- and belongs on tcgen05:
-//   * one CTA = one agent x one tile of 128 environments (M = 128 = the TMEM lanes);
+//   * one CTA = one agent x one tile of 128 environments (M = 128 = the TMEM lanes); the W2 chunks
+//     arrive by TMA bulk copies (cp.async.bulk, double buffered, counted on an mbarrier);
 //   * layer 1 (K = in_dim, tiny) on the CUDA cores, 32 hidden units at a time, written straight
 //     into shared memory as the A operand of the next layer: K-major, no swizzle, 8 x 16-byte core
 //     matrices (LBO = 128 rows x 16 B between k-groups of 4, SBO = 128 B between 8-row groups);
@@ -71,14 +72,33 @@ __device__ __forceinline__ void pol_mma(uint32_t tmem_d, uint64_t da, uint64_t d
 
 struct PolicySmem {
     float A_hi[8][128][4], A_lo[8][128][4];                 // layer-1 chunk, operand layout (2 x 16 KB)
-    float B[2][8][kPolNP][4];                                // W2 chunk hi / lo (2 x 38 KB)
+    float B[2][2][8][kPolNP][4];                             // two buffers of a W2 chunk, hi / lo (2 x 76 KB)
     float W1[kPolHidden][kPolMaxIn];                         // 19 KB
     float b1[kPolKP], b2[kPolNP];
-    float W3[kPolMaxA][kPolNP];                              // 19 KB
     float b3[kPolMaxA];
-    unsigned long long mbar;
+    unsigned long long full[2], mma_done;                    // mbarriers: W2 chunk landed / MMAs of a chunk done
     uint32_t tmem_base;
 };
+constexpr uint32_t kPolChunkBytes = 2 * 8 * kPolNP * 4 * sizeof(float);   // 77,824 B, contiguous in global memory
+
+__device__ __forceinline__ void pol_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 28)) __trap();                  // a lost arrival must fail loudly, not hang the device
+    }
+}
+// TMA bulk copy (1-D, no tensor map): one thread moves a whole W2 chunk global -> shared; the bytes are
+// counted on the mbarrier (complete_tx)
+__device__ __forceinline__ void pol_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    const uint32_t b = pol_smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pol_smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(b) : "memory");
+}
 
 template <typename Real>
 __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
@@ -97,10 +117,11 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
         sm.W1[idx / in_dim][idx % in_dim] = a.W1[(size_t)agent * kPolHidden * in_dim + idx];
     for (int idx = tid; idx < kPolKP; idx += 128) sm.b1[idx] = idx < kPolHidden ? a.b1[(size_t)agent * kPolHidden + idx] : 0.f;
     for (int idx = tid; idx < kPolNP; idx += 128) sm.b2[idx] = a.b2[(size_t)agent * kPolNP + idx];
-    for (int idx = tid; idx < A * kPolNP; idx += 128) sm.W3[idx / kPolNP][idx % kPolNP] = a.W3[(size_t)agent * A * kPolNP + idx];
     if (tid < A) sm.b3[tid] = a.b3[(size_t)agent * A + tid];
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mma_done)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -118,17 +139,19 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
 
-    // ---- layers 1 + 2, 32 hidden units of layer 1 (= 32 of K) at a time
-    const float4 *W2p = reinterpret_cast<const float4 *>(a.W2p) + (size_t)agent * (kPolKP / kPolChunk) * 2 * 8 * kPolNP;
-    uint32_t parity = 0;
-    for (int kc = 0; kc < kPolKP / kPolChunk; ++kc) {
-        // W2 chunk (already in operand layout, hi then lo): straight 16-byte copies
-        {
-            const float4 *src = W2p + (size_t)kc * 2 * 8 * kPolNP;
-            float4 *dst = reinterpret_cast<float4 *>(&sm.B[0][0][0][0]);
-            for (int idx = tid; idx < 2 * 8 * kPolNP; idx += 128) dst[idx] = src[idx];
-        }
+    // ---- layers 1 + 2, 32 hidden units of layer 1 (= 32 of K) at a time.  The W2 chunk of step kc + 2
+    // is in flight (TMA bulk copy into the buffer the MMAs of step kc have just released) while step
+    // kc + 1 computes layer 1 and runs its MMAs.
+    const float *W2p = a.W2p + (size_t)agent * (kPolKP / kPolChunk) * (kPolChunkBytes / sizeof(float));
+    constexpr int NCH = kPolKP / kPolChunk;
+    if (tid == 0) {
+        pol_bulk_load(&sm.B[0][0][0][0][0], W2p, kPolChunkBytes, &sm.full[0]);
+        pol_bulk_load(&sm.B[1][0][0][0][0], W2p + kPolChunkBytes / sizeof(float), kPolChunkBytes, &sm.full[1]);
+    }
+    for (int kc = 0; kc < NCH; ++kc) {
+        const int bsel = kc & 1;
         // layer 1 for this thread's environment: units 32 kc .. 32 kc + 31 (utils.py:289-290), split hi / lo
+        // (A_hi / A_lo are free: the MMAs of step kc - 1 were waited for at the end of that step)
 #pragma unroll
         for (int kg = 0; kg < 8; ++kg) {
             float hi[4], lo[4];
@@ -152,6 +175,7 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic stores -> async proxy
         __syncthreads();
         if (tid == 0) {
+            pol_wait(pol_smem_u32(&sm.full[bsel]), (uint32_t)(kc >> 1) & 1u);    // W2 chunk kc has landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {                                     // one MMA = K of 8 = 2 k-groups
@@ -160,8 +184,8 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {                           // N = 160 + 144
                     const int row0 = half ? 160 : 0, N = half ? 144 : 160;
-                    const uint64_t b_hi = pol_desc(&sm.B[0][2 * ks][row0][0], kPolNP * 16, 128);
-                    const uint64_t b_lo = pol_desc(&sm.B[1][2 * ks][row0][0], kPolNP * 16, 128);
+                    const uint64_t b_hi = pol_desc(&sm.B[bsel][0][2 * ks][row0][0], kPolNP * 16, 128);
+                    const uint64_t b_lo = pol_desc(&sm.B[bsel][1][2 * ks][row0][0], kPolNP * 16, 128);
                     const uint32_t idesc = pol_idesc(N), d = tmem + (uint32_t)row0;
                     pol_mma(d, a_hi, b_hi, idesc, (kc | ks) != 0);
                     pol_mma(d, a_hi, b_lo, idesc, 1);
@@ -169,19 +193,20 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                pol_smem_u32(&sm.mbar)));
+                pol_smem_u32(&sm.mma_done)));
         }
-        // the operands may be overwritten (and, after the last chunk, D read) once the MMAs are done
-        {
-            const uint32_t bar = pol_smem_u32(&sm.mbar);
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-            parity ^= 1;
-        }
+        // A_hi / A_lo and this W2 buffer may be overwritten (and, after the last step, D read) once the
+        // MMAs are done
+        pol_wait(pol_smem_u32(&sm.mma_done), (uint32_t)kc & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0 && kc + 2 < NCH)
+            pol_bulk_load(&sm.B[bsel][0][0][0][0], W2p + (size_t)(kc + 2) * (kPolChunkBytes / sizeof(float)), kPolChunkBytes,
+                          &sm.full[bsel]);
     }
+    // W3 of this agent -> the (now free) first W2 buffer, as [A][304]
+    float (*sW3)[kPolNP] = reinterpret_cast<float (*)[kPolNP]>(&sm.B[0][0][0][0][0]);
+    for (int idx = tid; idx < A * kPolNP; idx += 128) sW3[idx / kPolNP][idx % kPolNP] = a.W3[(size_t)agent * A * kPolNP + idx];
+    __syncthreads();
 
     // ---- epilogue: row e of D -> +b2, ReLU (utils.py:293-294) -> layer 3 on the CUDA cores (:297)
     float logit[kPolMaxA];
@@ -201,7 +226,7 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
             const float h2 = fmaxf(__uint_as_float(v[q]) + sm.b2[cidx], 0.f);     // padded columns: 0 + 0
 #pragma unroll
             for (int aa = 0; aa < kPolMaxA; ++aa)
-                if (aa < A) logit[aa] = fmaf(sm.W3[aa][cidx], h2, logit[aa]);
+                if (aa < A) logit[aa] = fmaf(sW3[aa][cidx], h2, logit[aa]);
         }
     }
     // softmax over the actions (utils.py:298), index by inverse CDF of a Philox uniform (:307)
