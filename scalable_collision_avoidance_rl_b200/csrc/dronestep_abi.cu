@@ -668,7 +668,7 @@ int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, in
 
 struct ds_policy {
     int n, in_dim, A, real_bytes, device;
-    float *W1 = nullptr, *b1 = nullptr, *W2p = nullptr, *b2 = nullptr, *W3 = nullptr, *b3 = nullptr;
+    float *head = nullptr, *W2p = nullptr, *W3t = nullptr;   // packed parameter blocks (dronestep_policy.cuh)
     void *atable = nullptr;
 };
 
@@ -688,10 +688,18 @@ int ds_policy_create(const ds_policy_config *cfg, ds_policy **out)
     const int n = cfg->n_agents, H = ds::kPolHidden, NP = ds::kPolNP, KP = ds::kPolKP, A = cfg->n_actions;
     // W2 -> [agent][chunk of 32 k][hi, lo][k-group of 4][304 rows][4]: the K-major core-matrix layout the
     // kernel's shared-memory descriptors describe; hi = the 19 bits kind::tf32 reads, lo = the rest
-    std::vector<float> w2p((size_t)n * (KP / 32) * 2 * 8 * NP * 4, 0.f), b2p((size_t)n * NP, 0.f), w3p((size_t)n * A * NP, 0.f);
+    // W1 (transposed), b1, b2, b3 -> one "head" block per agent; W3 -> transposed [304][16]
+    std::vector<float> w2p((size_t)n * (KP / 32) * 2 * 8 * NP * 4, 0.f), headp((size_t)n * ds::kPolHeadFloats, 0.f),
+        w3t((size_t)n * NP * ds::kPolMaxA, 0.f);
     for (int i = 0; i < n; ++i) {
+        float *hd = &headp[(size_t)i * ds::kPolHeadFloats];
+        for (int j = 0; j < H; ++j) {
+            for (int d = 0; d < cfg->in_dim; ++d) hd[ds::kPolHeadW1 + d * KP + j] = cfg->W1[((size_t)i * H + j) * cfg->in_dim + d];
+            hd[ds::kPolHeadB1 + j] = cfg->b1[(size_t)i * H + j];
+            hd[ds::kPolHeadB2 + j] = cfg->b2[(size_t)i * H + j];
+        }
+        for (int q = 0; q < ds::kPolMaxA; ++q) hd[ds::kPolHeadB3 + q] = q < A ? cfg->b3[(size_t)i * A + q] : -INFINITY;
         for (int r = 0; r < H; ++r) {
-            b2p[(size_t)i * NP + r] = cfg->b2[(size_t)i * H + r];
             for (int k = 0; k < H; ++k) {
                 const float w = cfg->W2[((size_t)i * H + r) * H + k];
                 uint32_t bits; std::memcpy(&bits, &w, 4);
@@ -704,7 +712,8 @@ int ds_policy_create(const ds_policy_config *cfg, ds_policy **out)
             }
         }
         for (int aidx = 0; aidx < A; ++aidx)
-            for (int k = 0; k < H; ++k) w3p[((size_t)i * A + aidx) * NP + k] = cfg->W3[((size_t)i * A + aidx) * H + k];
+            for (int k = 0; k < H; ++k)
+                w3t[((size_t)i * NP + k) * ds::kPolMaxA + aidx] = cfg->W3[((size_t)i * A + aidx) * H + k];
     }
     ds_policy *p = new ds_policy();
     p->n = n; p->in_dim = cfg->in_dim; p->A = A; p->real_bytes = cfg->real_bytes; p->device = cfg->device;
@@ -712,12 +721,9 @@ int ds_policy_create(const ds_policy_config *cfg, ds_policy **out)
         cudaError_t e = cudaMalloc((void **)dst, count * sizeof(float));
         return e != cudaSuccess ? e : cudaMemcpy(*dst, src, count * sizeof(float), cudaMemcpyHostToDevice);
     };
-    cudaError_t e = up(&p->W1, cfg->W1, (size_t)n * H * cfg->in_dim);
-    if (e == cudaSuccess) e = up(&p->b1, cfg->b1, (size_t)n * H);
+    cudaError_t e = up(&p->head, headp.data(), headp.size());
     if (e == cudaSuccess) e = up(&p->W2p, w2p.data(), w2p.size());
-    if (e == cudaSuccess) e = up(&p->b2, b2p.data(), b2p.size());
-    if (e == cudaSuccess) e = up(&p->W3, w3p.data(), w3p.size());
-    if (e == cudaSuccess) e = up(&p->b3, cfg->b3, (size_t)n * A);
+    if (e == cudaSuccess) e = up(&p->W3t, w3t.data(), w3t.size());
     if (e == cudaSuccess) e = cudaMalloc(&p->atable, (size_t)A * 2 * cfg->real_bytes);
     if (e == cudaSuccess) {
         if (cfg->real_bytes == 8) e = cudaMemcpy(p->atable, cfg->action_table, (size_t)A * 16, cudaMemcpyHostToDevice);
@@ -736,7 +742,7 @@ void ds_policy_destroy(ds_policy *p)
 {
     if (!p) return;
     DeviceGuard guard(p->device);
-    cudaFree(p->W1); cudaFree(p->b1); cudaFree(p->W2p); cudaFree(p->b2); cudaFree(p->W3); cudaFree(p->b3); cudaFree(p->atable);
+    cudaFree(p->head); cudaFree(p->W2p); cudaFree(p->W3t); cudaFree(p->atable);
     delete p;
 }
 
@@ -752,18 +758,26 @@ int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void
     ds::PolicyArgs a;
     a.E = h->E; a.n = h->n; a.in_dim = pol->in_dim; a.n_actions = pol->A; a.real_bytes = h->real_bytes;
     a.seed_lo = (unsigned)io->seed; a.seed_hi = (unsigned)(io->seed >> 32); a.stream = io->stream;
-    a.z = io->z; a.W1 = pol->W1; a.b1 = pol->b1; a.W2p = pol->W2p; a.b2 = pol->b2; a.W3 = pol->W3; a.b3 = pol->b3;
+    a.z = io->z; a.head = pol->head; a.W2p = pol->W2p; a.W3t = pol->W3t;
     a.atable = pol->atable; a.act = io->actions; a.aidx = io->action_idx; a.probs = io->probs;
     const dim3 grid((h->E + 127) / 128, h->n);
     const size_t smem = sizeof(ds::PolicySmem) + 128;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+#define DS_POLICY_LAUNCH(REAL, IN)                                                                      \
+    do {                                                                                                \
+        DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<REAL, IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                       \
+        ds::policy_kernel<REAL, IN><<<grid, 128, smem, st>>>(a);                                        \
+    } while (0)
+    const int in_sel = (pol->in_dim == 6) ? 6 : (pol->in_dim == 15 ? 15 : 0);
     if (h->real_bytes == 8) {
-        DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ds::policy_kernel<double><<<grid, 128, smem, st>>>(a);
+        if (in_sel == 6) DS_POLICY_LAUNCH(double, 6); else if (in_sel == 15) DS_POLICY_LAUNCH(double, 15);
+        else DS_POLICY_LAUNCH(double, 0);
     } else {
-        DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ds::policy_kernel<float><<<grid, 128, smem, st>>>(a);
+        if (in_sel == 6) DS_POLICY_LAUNCH(float, 6); else if (in_sel == 15) DS_POLICY_LAUNCH(float, 15);
+        else DS_POLICY_LAUNCH(float, 0);
     }
+#undef DS_POLICY_LAUNCH
     DS_CUDA(cudaGetLastError());
     return DS_OK;
 }

@@ -10,9 +10,10 @@
 // agent), M = E rows each -- and belongs on tcgen05:
 //   * one CTA = one agent x one tile of 128 environments (M = 128 = the TMEM lanes); the W2 chunks
 //     arrive by TMA bulk copies (cp.async.bulk, double buffered, counted on an mbarrier);
-//   * layer 1 (K = in_dim, tiny) on the CUDA cores, 32 hidden units at a time, written straight
+//   * layer 1 (K = in_dim, tiny) on the CUDA cores, 16 hidden units at a time, written straight
 //     into shared memory as the A operand of the next layer: K-major, no swizzle, 8 x 16-byte core
 //     matrices (LBO = 128 rows x 16 B between k-groups of 4, SBO = 128 B between 8-row groups);
+//     two such half-chunks alternate, so the MMAs of one run while the next is computed;
 //   * layer 2 as tcgen05.mma.kind::tf32 with the accumulator D[128 x 304] in TMEM; fp32 parity is
 //     kept by the 3xTF32 split: x = hi + lo with hi = the 19 bits the tensor core reads,
 //     D += A_hi B_hi + A_hi B_lo + A_lo B_hi (relative error ~2^-20 instead of 2^-10);  W2 is
@@ -32,14 +33,20 @@ constexpr int kPolKP = 320;           // K of layer 2 padded to whole chunks of 
 constexpr int kPolChunk = 32;         // hidden units of layer 1 produced per staging round
 constexpr int kPolMaxIn = 16, kPolMaxA = 16;
 
+// per-agent parameter block ("head"), packed by ds_policy_create so that one bulk copy brings it in
+constexpr int kPolHeadW1 = 0;                                  // W1 transposed [16 inputs][320 units], zero padded
+constexpr int kPolHeadB1 = kPolMaxIn * kPolKP;                 // b1 [320], zero padded
+constexpr int kPolHeadB2 = kPolHeadB1 + kPolKP;                // b2 [304], zero padded
+constexpr int kPolHeadB3 = kPolHeadB2 + kPolNP;                // b3 [16], -inf padded
+constexpr int kPolHeadFloats = kPolHeadB3 + kPolMaxA;          // 5760 floats = 23,040 B
+
 struct PolicyArgs {
     int E, n, in_dim, n_actions, real_bytes;
     unsigned seed_lo, seed_hi, stream;
     const void *z;            // Real [E][n][in_dim]
-    const float *W1, *b1;     // [n][300][in_dim], [n][300]
+    const float *head;        // [n][kPolHeadFloats]
     const float *W2p;         // [n][10 chunks][2 (hi, lo)][8 k-groups][304 rows][4]   operand layout
-    const float *b2;          // [n][304] (zero padded)
-    const float *W3, *b3;     // [n][A][304] (zero padded), [n][A]
+    const float *W3t;         // [n][304][16]: W3 transposed, zero padded
     const void *atable;       // Real [A][2]
     void *act;                // Real [E][n][2] out
     uint8_t *aidx;            // [E][n] out (may be null)
@@ -71,15 +78,19 @@ __device__ __forceinline__ void pol_mma(uint32_t tmem_d, uint64_t da, uint64_t d
 }
 
 struct PolicySmem {
-    float A_hi[8][128][4], A_lo[8][128][4];                 // layer-1 chunk, operand layout (2 x 16 KB)
+    float A_hi[2][4][128][4], A_lo[2][4][128][4];           // two half-chunks (16 units) of layer 1, operand layout (32 KB)
     float B[2][2][8][kPolNP][4];                             // two buffers of a W2 chunk, hi / lo (2 x 76 KB)
-    float W1[kPolHidden][kPolMaxIn];                         // 19 KB
-    float b1[kPolKP], b2[kPolNP];
-    float b3[kPolMaxA];
-    unsigned long long full[2], mma_done;                    // mbarriers: W2 chunk landed / MMAs of a chunk done
+    float W1t[kPolMaxIn][kPolKP];                            // the head block, in ds_policy_create's order (22.5 KB)
+    float b1[kPolKP], b2[kPolNP], b3[kPolMaxA];
+    float W3t[kPolNP][kPolMaxA];                             // 19 KB
+    unsigned long long full[2], mma_done[2], params;         // mbarriers: W2 chunk landed / MMAs of a half-chunk done / head + W3t landed
     uint32_t tmem_base;
 };
+static_assert(offsetof(PolicySmem, b1) - offsetof(PolicySmem, W1t) == kPolHeadB1 * sizeof(float) &&
+              offsetof(PolicySmem, b2) - offsetof(PolicySmem, W1t) == kPolHeadB2 * sizeof(float) &&
+              offsetof(PolicySmem, b3) - offsetof(PolicySmem, W1t) == kPolHeadB3 * sizeof(float), "head block layout");
 constexpr uint32_t kPolChunkBytes = 2 * 8 * kPolNP * 4 * sizeof(float);   // 77,824 B, contiguous in global memory
+constexpr uint32_t kPolHeadBytes = kPolHeadFloats * sizeof(float), kPolW3tBytes = kPolNP * kPolMaxA * sizeof(float);
 
 __device__ __forceinline__ void pol_wait(uint32_t bar, uint32_t parity)
 {
@@ -90,17 +101,61 @@ __device__ __forceinline__ void pol_wait(uint32_t bar, uint32_t parity)
         if (spins > (1u << 28)) __trap();                  // a lost arrival must fail loudly, not hang the device
     }
 }
-// TMA bulk copy (1-D, no tensor map): one thread moves a whole W2 chunk global -> shared; the bytes are
-// counted on the mbarrier (complete_tx)
+// TMA bulk copies (1-D, no tensor map): one thread moves a whole block global -> shared; the bytes are
+// counted on the mbarrier (expect_tx / complete_tx)
+__device__ __forceinline__ void pol_expect(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pol_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pol_bulk_copy(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     pol_smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(pol_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void pol_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
-    const uint32_t b = pol_smem_u32(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     pol_smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(b) : "memory");
+    pol_expect(bar, bytes);
+    pol_bulk_copy(dst, src, bytes, bar);
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane (asynchronous: pol_ld_wait before use)
+__device__ __forceinline__ void pol_ld16(uint32_t (&v)[16], uint32_t taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void pol_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// +b2, ReLU (utils.py:293-294) and layer 3 (:297) for 16 columns of the row: two actions per FFMA2
+__device__ __forceinline__ void pol_layer3_block(float2 (&lg)[kPolMaxA / 2], const uint32_t (&v)[16], int c0,
+                                                 const PolicySmem &sm, bool wide)
+{
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int cidx = c0 + q;
+        const float h2 = fmaxf(__uint_as_float(v[q]) + sm.b2[cidx], 0.f);         // padded columns: 0 + 0
+        const float2 hh = make_float2(h2, h2);
+        const float4 w0 = *reinterpret_cast<const float4 *>(&sm.W3t[cidx][0]);
+        const float4 w1 = *reinterpret_cast<const float4 *>(&sm.W3t[cidx][4]);
+        lg[0] = __ffma2_rn(make_float2(w0.x, w0.y), hh, lg[0]);
+        lg[1] = __ffma2_rn(make_float2(w0.z, w0.w), hh, lg[1]);
+        lg[2] = __ffma2_rn(make_float2(w1.x, w1.y), hh, lg[2]);
+        lg[3] = __ffma2_rn(make_float2(w1.z, w1.w), hh, lg[3]);
+        if (wide) {
+            const float4 w2 = *reinterpret_cast<const float4 *>(&sm.W3t[cidx][8]);
+            const float4 w3 = *reinterpret_cast<const float4 *>(&sm.W3t[cidx][12]);
+            lg[4] = __ffma2_rn(make_float2(w2.x, w2.y), hh, lg[4]);
+            lg[5] = __ffma2_rn(make_float2(w2.z, w2.w), hh, lg[5]);
+            lg[6] = __ffma2_rn(make_float2(w3.x, w3.y), hh, lg[6]);
+            lg[7] = __ffma2_rn(make_float2(w3.z, w3.w), hh, lg[7]);
+        }
+    }
 }
 
-template <typename Real>
+// IN = in_dim when it is one of the reference's two observation widths (6: simplify_zstate, 15: full,
+// k = 2), else 0 (any in_dim <= 16, guarded loop).  Layers 1 and 3 run on the packed-f32 pipe
+// (FFMA2: two hidden units / two actions per instruction, operands read as float4).
+template <typename Real, int IN>
 __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
 {
     using V2 = typename vec2_of<Real>::type;
@@ -112,17 +167,20 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
     const bool live = e < a.E;
     const int in_dim = a.in_dim, A = a.n_actions;
 
-    // ---- per-agent parameters -> shared memory
-    for (int idx = tid; idx < kPolHidden * in_dim; idx += 128)
-        sm.W1[idx / in_dim][idx % in_dim] = a.W1[(size_t)agent * kPolHidden * in_dim + idx];
-    for (int idx = tid; idx < kPolKP; idx += 128) sm.b1[idx] = idx < kPolHidden ? a.b1[(size_t)agent * kPolHidden + idx] : 0.f;
-    for (int idx = tid; idx < kPolNP; idx += 128) sm.b2[idx] = a.b2[(size_t)agent * kPolNP + idx];
-    if (tid < A) sm.b3[tid] = a.b3[(size_t)agent * A + tid];
+    // ---- mbarriers, TMEM, and the first copies: parameter block + W3t, W2 chunks 0 and 1
+    const float *W2p = a.W2p + (size_t)agent * (kPolKP / kPolChunk) * (kPolChunkBytes / sizeof(float));
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[1])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mma_done)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mma_done[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mma_done[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.params)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pol_expect(&sm.params, kPolHeadBytes + kPolW3tBytes);
+        pol_bulk_copy(&sm.W1t[0][0], a.head + (size_t)agent * kPolHeadFloats, kPolHeadBytes, &sm.params);
+        pol_bulk_copy(&sm.W3t[0][0], a.W3t + (size_t)agent * kPolNP * kPolMaxA, kPolW3tBytes, &sm.params);
+        pol_bulk_load(&sm.B[0][0][0][0][0], W2p, kPolChunkBytes, &sm.full[0]);
+        pol_bulk_load(&sm.B[1][0][0][0][0], W2p + kPolChunkBytes / sizeof(float), kPolChunkBytes, &sm.full[1]);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pol_smem_u32(&sm.tmem_base)),
@@ -138,97 +196,99 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
+    pol_wait(pol_smem_u32(&sm.params), 0u);
 
-    // ---- layers 1 + 2, 32 hidden units of layer 1 (= 32 of K) at a time.  The W2 chunk of step kc + 2
-    // is in flight (TMA bulk copy into the buffer the MMAs of step kc have just released) while step
-    // kc + 1 computes layer 1 and runs its MMAs.
-    const float *W2p = a.W2p + (size_t)agent * (kPolKP / kPolChunk) * (kPolChunkBytes / sizeof(float));
-    constexpr int NCH = kPolKP / kPolChunk;
-    if (tid == 0) {
-        pol_bulk_load(&sm.B[0][0][0][0][0], W2p, kPolChunkBytes, &sm.full[0]);
-        pol_bulk_load(&sm.B[1][0][0][0][0], W2p + kPolChunkBytes / sizeof(float), kPolChunkBytes, &sm.full[1]);
-    }
-    for (int kc = 0; kc < NCH; ++kc) {
-        const int bsel = kc & 1;
-        // layer 1 for this thread's environment: units 32 kc .. 32 kc + 31 (utils.py:289-290), split hi / lo
-        // (A_hi / A_lo are free: the MMAs of step kc - 1 were waited for at the end of that step)
+    // ---- layers 1 + 2 in 20 half-chunks of 16 hidden units (= 16 of K).  Step s computes layer 1 into
+    // A half (s & 1) while the MMAs of step s - 1 run from the other half; W2 arrives in chunks of 32
+    // (two steps), the chunk of step s + 4 being copied while steps s + 2, s + 3 compute.
+    constexpr int NST = 2 * (kPolKP / kPolChunk);
+    for (int s_ = 0; s_ < NST; ++s_) {
+        const int ab = s_ & 1, kc = s_ >> 1, bsel = kc & 1;
+        // A half ab was last read by the MMAs of step s - 2
+        if (s_ >= 2) pol_wait(pol_smem_u32(&sm.mma_done[ab]), (uint32_t)((s_ >> 1) - 1) & 1u);
+        // layer 1 for this thread's environment: units 16 s .. 16 s + 15 (utils.py:289-290), split hi / lo
 #pragma unroll
-        for (int kg = 0; kg < 8; ++kg) {
+        for (int kg = 0; kg < 4; ++kg) {
+            const int j0 = s_ * 16 + kg * 4;                                     // units j0 .. j0 + 3 (padding: 0 weights)
+            const float4 bb = *reinterpret_cast<const float4 *>(&sm.b1[j0]);
+            float2 h01 = make_float2(bb.x, bb.y), h23 = make_float2(bb.z, bb.w);
+#pragma unroll
+            for (int d = 0; d < (IN > 0 ? IN : kPolMaxIn); ++d) {
+                if (IN > 0 || d < in_dim) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&sm.W1t[d][j0]);
+                    const float2 zz = make_float2(zin[d], zin[d]);
+                    h01 = __ffma2_rn(make_float2(w.x, w.y), zz, h01);
+                    h23 = __ffma2_rn(make_float2(w.z, w.w), zz, h23);
+                }
+            }
+            const float h[4] = {fmaxf(h01.x, 0.f), fmaxf(h01.y, 0.f), fmaxf(h23.x, 0.f), fmaxf(h23.y, 0.f)};
             float hi[4], lo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int j = kc * kPolChunk + kg * 4 + q;
-                float h = 0.f;
-                if (j < kPolHidden) {
-                    h = sm.b1[j];
-#pragma unroll
-                    for (int d = 0; d < kPolMaxIn; ++d)
-                        if (d < in_dim) h = fmaf(sm.W1[j][d], zin[d], h);
-                    h = fmaxf(h, 0.f);
-                }
-                hi[q] = __uint_as_float(__float_as_uint(h) & 0xffffe000u);       // what kind::tf32 reads
-                lo[q] = h - hi[q];                                               // exact
+                hi[q] = __uint_as_float(__float_as_uint(h[q]) & 0xffffe000u);    // what kind::tf32 reads
+                lo[q] = h[q] - hi[q];                                            // exact
             }
-            *reinterpret_cast<float4 *>(&sm.A_hi[kg][tid][0]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(&sm.A_lo[kg][tid][0]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4 *>(&sm.A_hi[ab][kg][tid][0]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4 *>(&sm.A_lo[ab][kg][tid][0]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic stores -> async proxy
         __syncthreads();
         if (tid == 0) {
-            pol_wait(pol_smem_u32(&sm.full[bsel]), (uint32_t)(kc >> 1) & 1u);    // W2 chunk kc has landed
+            if (ab == 0) pol_wait(pol_smem_u32(&sm.full[bsel]), (uint32_t)(kc >> 1) & 1u);   // W2 chunk kc has landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {                                     // one MMA = K of 8 = 2 k-groups
-                const uint64_t a_hi = pol_desc(&sm.A_hi[2 * ks][0][0], 128 * 16, 128);
-                const uint64_t a_lo = pol_desc(&sm.A_lo[2 * ks][0][0], 128 * 16, 128);
+            for (int ks = 0; ks < 2; ++ks) {                                     // one MMA = K of 8 = 2 k-groups
+                const uint64_t a_hi = pol_desc(&sm.A_hi[ab][2 * ks][0][0], 128 * 16, 128);
+                const uint64_t a_lo = pol_desc(&sm.A_lo[ab][2 * ks][0][0], 128 * 16, 128);
+                const int kgb = 4 * ab + 2 * ks;                                 // k-group inside the W2 chunk
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {                           // N = 160 + 144
                     const int row0 = half ? 160 : 0, N = half ? 144 : 160;
-                    const uint64_t b_hi = pol_desc(&sm.B[bsel][0][2 * ks][row0][0], kPolNP * 16, 128);
-                    const uint64_t b_lo = pol_desc(&sm.B[bsel][1][2 * ks][row0][0], kPolNP * 16, 128);
+                    const uint64_t b_hi = pol_desc(&sm.B[bsel][0][kgb][row0][0], kPolNP * 16, 128);
+                    const uint64_t b_lo = pol_desc(&sm.B[bsel][1][kgb][row0][0], kPolNP * 16, 128);
                     const uint32_t idesc = pol_idesc(N), d = tmem + (uint32_t)row0;
-                    pol_mma(d, a_hi, b_hi, idesc, (kc | ks) != 0);
+                    pol_mma(d, a_hi, b_hi, idesc, (s_ | ks) != 0);
                     pol_mma(d, a_hi, b_lo, idesc, 1);
                     pol_mma(d, a_lo, b_hi, idesc, 1);
                 }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                pol_smem_u32(&sm.mma_done)));
+                pol_smem_u32(&sm.mma_done[ab])));
+            // the MMAs of step s - 1 (issued a whole layer-1 pass ago) were the last readers of the W2
+            // buffer of chunk kc - 1 when s is even: refill it with chunk kc + 1
+            if (ab == 0 && s_ >= 2 && kc + 1 < NST / 2) {
+                pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((s_ - 1) >> 1) & 1u);
+                pol_bulk_load(&sm.B[bsel ^ 1][0][0][0][0], W2p + (size_t)(kc + 1) * (kPolChunkBytes / sizeof(float)),
+                              kPolChunkBytes, &sm.full[bsel ^ 1]);
+            }
         }
-        // A_hi / A_lo and this W2 buffer may be overwritten (and, after the last step, D read) once the
-        // MMAs are done
-        pol_wait(pol_smem_u32(&sm.mma_done), (uint32_t)kc & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 0 && kc + 2 < NCH)
-            pol_bulk_load(&sm.B[bsel][0][0][0][0], W2p + (size_t)(kc + 2) * (kPolChunkBytes / sizeof(float)), kPolChunkBytes,
-                          &sm.full[bsel]);
     }
-    // W3 of this agent -> the (now free) first W2 buffer, as [A][304]
-    float (*sW3)[kPolNP] = reinterpret_cast<float (*)[kPolNP]>(&sm.B[0][0][0][0][0]);
-    for (int idx = tid; idx < A * kPolNP; idx += 128) sW3[idx / kPolNP][idx % kPolNP] = a.W3[(size_t)agent * A * kPolNP + idx];
-    __syncthreads();
+    // D may be read once the MMAs of the last step (and with them all earlier ones) are done
+    pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((NST - 1) >> 1) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: row e of D -> +b2, ReLU (utils.py:293-294) -> layer 3 on the CUDA cores (:297)
+    // ---- epilogue: row e of D -> +b2, ReLU -> layer 3 on the CUDA cores; the tcgen05.ld of the next
+    // 16 columns is in flight while the current 16 are folded into the logits
+    float2 lg[kPolMaxA / 2];                                                   // logits, two actions per register pair
+#pragma unroll
+    for (int q = 0; q < kPolMaxA / 2; ++q) lg[q] = make_float2(sm.b3[2 * q], sm.b3[2 * q + 1]);   // -inf beyond A
+    const bool wide = A > 8;                                                   // uniform: second half of the actions
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t va[16], vb[16];
+    pol_ld16(va, trow);
+    for (int c0 = 0; c0 < kPolNP; c0 += 32) {                                  // 19 blocks of 16: 9 pairs + 1
+        pol_ld_wait();
+        if (c0 + 16 < kPolNP) pol_ld16(vb, trow + (uint32_t)(c0 + 16));
+        pol_layer3_block(lg, va, c0, sm, wide);
+        if (c0 + 16 < kPolNP) {
+            pol_ld_wait();
+            if (c0 + 32 < kPolNP) pol_ld16(va, trow + (uint32_t)(c0 + 32));
+            pol_layer3_block(lg, vb, c0 + 16, sm, wide);
+        }
+    }
     float logit[kPolMaxA];
 #pragma unroll
-    for (int q = 0; q < kPolMaxA; ++q) logit[q] = (q < A) ? sm.b3[q] : -INFINITY;
-    for (int c0 = 0; c0 < kPolNP; c0 += 16) {
-        uint32_t v[16];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int cidx = c0 + q;
-            const float h2 = fmaxf(__uint_as_float(v[q]) + sm.b2[cidx], 0.f);     // padded columns: 0 + 0
-#pragma unroll
-            for (int aa = 0; aa < kPolMaxA; ++aa)
-                if (aa < A) logit[aa] = fmaf(sW3[aa][cidx], h2, logit[aa]);
-        }
-    }
+    for (int q = 0; q < kPolMaxA / 2; ++q) { logit[2 * q] = lg[q].x; logit[2 * q + 1] = lg[q].y; }
     // softmax over the actions (utils.py:298), index by inverse CDF of a Philox uniform (:307)
     float mx = -INFINITY;
 #pragma unroll
