@@ -233,6 +233,27 @@ typedef struct ds_policy_io {
 } ds_policy_io;
 int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void *cuda_stream);
 
+/* A whole closed-loop episode with the actors on the device -- the loop of
+ * train_problem.py:82-104 (`actions = agents.forward(z_states, Ni)`; `env.step(actions)`) for E
+ * environments, 2 T launches enqueued on the stream, no host round trip and no synchronisation
+ * (capturable in a CUDA graph after one warm-up call).  Step t draws its actions with
+ * ds_policy_forward on the live observation io->z (stream = stream0 + t), then steps with
+ * ds_rollout's semantics: done environments are skipped (finished code 2), a finishing environment
+ * sets done[e], agg accumulates the episode sums, the live buffers of io hold the last executed
+ * step.  ro names the trajectory buffers as for ds_rollout (ro->actions / action_idx must be NULL;
+ * the actions taken are recorded in vel_tr, state[:,2:4] = u).  io->z must hold the observation
+ * of the current state on entry (ds_observe / ds_reset_random / a previous step). */
+typedef struct ds_policy_rollout_io {
+    uint8_t *action_idx_tr;    /* out u8 [T][E][n]: the drawn indices (may be NULL) */
+    float *probs_tr;           /* out f32 [T][E][n][A] (may be NULL) */
+    uint64_t seed;
+    const uint64_t *seed_dev;  /* device pointer; when non-NULL it overrides seed (graph replays) */
+    uint32_t stream0;
+    uint32_t _pad;
+} ds_policy_rollout_io;
+int ds_rollout_policy(ds_handle *h, ds_policy *pol, const ds_params *p, const ds_buffers *io,
+                      const ds_rollout_io *ro, const ds_policy_rollout_io *pio, void *cuda_stream);
+
 /* One step with HOST action / result buffers holding Real of the handle's
  * precision (pinned memory recommended): H2D actions -> ds_step -> D2H of the
  * reference's 6-tuple (drone_env.py:258), then one stream synchronise.  Output

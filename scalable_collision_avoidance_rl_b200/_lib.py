@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "ds_default_params", "ds_step", "ds_observe", "ds_rollout", "ds_reduce_aggregates",
     "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_rollout_host", "ds_returns",
     "ds_step_control", "ds_rollout_control", "ds_reset_random",
-    "ds_policy_create", "ds_policy_destroy", "ds_policy_forward",
+    "ds_policy_create", "ds_policy_destroy", "ds_policy_forward", "ds_rollout_policy",
 )
 
 
@@ -73,6 +73,11 @@ class ds_policy_config(ctypes.Structure):
 class ds_policy_io(ctypes.Structure):
     _fields_ = [("z", c_void_p), ("actions", c_void_p), ("action_idx", c_void_p), ("probs", c_void_p),
                 ("seed", ctypes.c_uint64), ("stream", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
+
+
+class ds_policy_rollout_io(ctypes.Structure):
+    _fields_ = [("action_idx_tr", c_void_p), ("probs_tr", c_void_p), ("seed", ctypes.c_uint64),
+                ("seed_dev", c_void_p), ("stream0", ctypes.c_uint32), ("_pad", ctypes.c_uint32)]
 
 
 class ds_host_step_out(ctypes.Structure):

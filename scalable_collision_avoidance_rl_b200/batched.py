@@ -454,6 +454,56 @@ class BatchedDrones:
                    "ds_policy_forward")
         return self.actions, self.action_idx, (self.action_probs if want_probs else None)
 
+    def rollout_policy(self, T, seed=0, stream0=0, record=("reward", "true_reward", "obs", "ncoll", "finished",
+                                                          "action_idx"), out=None, seed_tensor=None):
+        """A closed-loop episode with the loaded actors, entirely on the device (ds_rollout_policy):
+        for t < T: `actions = agents.forward(z_states, Ni)` then `env.step(actions)`
+        (train_problem.py:82-104) for every environment -- 2 T launches on the current stream, no
+        host round trip.  Semantics and outputs as rollout(): finished environments stop, `finished`
+        codes 0 / 1 / 2, agg / done; "vel" records the actions taken, "action_idx" the drawn
+        indices [T,E,n] (what log_p_of_a needs, utils.py:311-318), "probs" the distributions.
+        Step t samples from Philox(seed; e, i, stream0 + t); seed_tensor (uint64 device tensor of
+        one element) overrides seed, so that a captured CUDA graph can be replayed with new draws."""
+        assert getattr(self, "_pol", None) is not None and self._pol.value, "load_policy() first"
+        E, n, k = self.n_envs, self.n_agents, self.k_closest
+        out = {} if out is None else out
+        dev, dt_ = self.device, self.dtype
+
+        def buf(name, shape, dtype):
+            t = out.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                out[name] = t
+            return t
+
+        rec = set(record)
+        ro = _lib.ds_rollout_io()
+        ro.T = int(T)
+        if "pos" in rec: ro.pos_tr = buf("pos", (T, E, n, 2), dt_).data_ptr()
+        if "vel" in rec: ro.vel_tr = buf("vel", (T, E, n, 2), dt_).data_ptr()
+        if "reward" in rec: ro.reward_tr = buf("reward", (T, E, n), dt_).data_ptr()
+        if "true_reward" in rec: ro.true_reward_tr = buf("true_reward", (T, E, n), dt_).data_ptr()
+        if "obs" in rec:
+            ro.z_tr = buf("z", (T, E, n, k + 1, self.cols), dt_).data_ptr()
+            ro.Ni_tr = buf("Ni", (T, E, n, k + 1), torch.int32).data_ptr()
+        if "ncoll" in rec: ro.ncoll_tr = buf("ncoll", (T, E), torch.int32).data_ptr()
+        if "finished" in rec: ro.finished_tr = buf("finished", (T, E), torch.uint8).data_ptr()
+        ro.agg = self.agg.data_ptr()
+        ro.done = self.done.data_ptr()
+        pio = _lib.ds_policy_rollout_io()
+        if "action_idx" in rec: pio.action_idx_tr = buf("action_idx", (T, E, n), torch.uint8).data_ptr()
+        if "probs" in rec: pio.probs_tr = buf("probs", (T, E, n, self._pol_A), torch.float32).data_ptr()
+        pio.seed = int(seed); pio.stream0 = int(stream0)
+        if seed_tensor is not None:
+            assert seed_tensor.is_cuda and seed_tensor.dtype == torch.uint64 and seed_tensor.numel() == 1
+            pio.seed_dev = seed_tensor.data_ptr()
+        p = self._params()
+        _lib.check(self.lib.ds_rollout_policy(self._h, self._pol, ctypes.byref(p), ctypes.byref(self._io),
+                                              ctypes.byref(ro), ctypes.byref(pio), self._stream()),
+                   "ds_rollout_policy")
+        out["agg"], out["done"] = self.agg, self.done
+        return out
+
     def episode_aggregates(self):
         """Device-side sum over this rank's environments of the per-env episode accumulators
         -> float64 [5] = (sum_t mean_i r, sum_t mean_i true_r, sum_t collisions, steps, #envs):

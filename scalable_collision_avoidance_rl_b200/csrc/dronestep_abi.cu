@@ -439,6 +439,12 @@ int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params 
     return launch_step(h, a, (cudaStream_t)cuda_stream);
 }
 
+static int launch_rollout_control(ds_handle *h, const ds::RolloutArgs &ra, const Geom &gm, cudaStream_t st)
+{
+    if (h->real_bytes == 8) { DS_DISPATCH_NT(rollout_control_kernel, double, ra, gm) }
+    else { DS_DISPATCH_NT(rollout_control_kernel, float, ra, gm) }
+}
+
 int ds_rollout_control(ds_handle *h, int controller, double u_max, const ds_params *p, const ds_buffers *io,
                        const ds_rollout_io *ro, void *cuda_stream)
 {
@@ -462,8 +468,7 @@ int ds_rollout_control(ds_handle *h, int controller, double u_max, const ds_para
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const Geom gm{h->step_blocks, h->step_threads, h->step_smem};
-    if (h->real_bytes == 8) { DS_DISPATCH_NT(rollout_control_kernel, double, ra, gm) }
-    else { DS_DISPATCH_NT(rollout_control_kernel, float, ra, gm) }
+    return launch_rollout_control(h, ra, gm, st);
 }
 
 int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream)
@@ -746,23 +751,20 @@ void ds_policy_destroy(ds_policy *p)
     delete p;
 }
 
-int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void *cuda_stream)
+static int check_policy(const char *who, ds_handle *h, ds_policy *pol)
 {
-    if (!h || !pol || !io || !io->z || !io->actions) return fail(DS_ERR_ARG, "ds_policy_forward: NULL argument");
-    if (pol->n != h->n) return fail(DS_ERR_ARG, "ds_policy_forward: the policy has a different number of agents");
+    if (pol->n != h->n) return fail(DS_ERR_ARG, std::string(who) + ": the policy has a different number of agents");
     if (pol->real_bytes != h->real_bytes || pol->device != h->device)
-        return fail(DS_ERR_ARG, "ds_policy_forward: the policy was created for another precision / device");
+        return fail(DS_ERR_ARG, std::string(who) + ": the policy was created for another precision / device");
     if (pol->in_dim != (h->k + 1) * (h->simplify ? 2 : 5))
-        return fail(DS_ERR_ARG, "ds_policy_forward: in_dim != (k + 1) * cols of the observation");
-    DeviceGuard guard(h->device);
-    ds::PolicyArgs a;
-    a.E = h->E; a.n = h->n; a.in_dim = pol->in_dim; a.n_actions = pol->A; a.real_bytes = h->real_bytes;
-    a.seed_lo = (unsigned)io->seed; a.seed_hi = (unsigned)(io->seed >> 32); a.stream = io->stream;
-    a.z = io->z; a.head = pol->head; a.W2p = pol->W2p; a.W3t = pol->W3t;
-    a.atable = pol->atable; a.act = io->actions; a.aidx = io->action_idx; a.probs = io->probs;
+        return fail(DS_ERR_ARG, std::string(who) + ": in_dim != (k + 1) * cols of the observation");
+    return DS_OK;
+}
+
+static int launch_policy(ds_handle *h, ds_policy *pol, const ds::PolicyArgs &a, cudaStream_t st)
+{
     const dim3 grid((h->E + 127) / 128, h->n);
     const size_t smem = sizeof(ds::PolicySmem) + 128;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
 #define DS_POLICY_LAUNCH(REAL, IN)                                                                      \
     do {                                                                                                \
         DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<REAL, IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -779,6 +781,80 @@ int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void
     }
 #undef DS_POLICY_LAUNCH
     DS_CUDA(cudaGetLastError());
+    return DS_OK;
+}
+
+static ds::PolicyArgs policy_args(ds_handle *h, ds_policy *pol)
+{
+    ds::PolicyArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.E = h->E; a.n = h->n; a.in_dim = pol->in_dim; a.n_actions = pol->A; a.real_bytes = h->real_bytes;
+    a.head = pol->head; a.W2p = pol->W2p; a.W3t = pol->W3t; a.atable = pol->atable;
+    return a;
+}
+
+int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void *cuda_stream)
+{
+    if (!h || !pol || !io || !io->z || !io->actions) return fail(DS_ERR_ARG, "ds_policy_forward: NULL argument");
+    if (int rc = check_policy("ds_policy_forward", h, pol)) return rc;
+    DeviceGuard guard(h->device);
+    ds::PolicyArgs a = policy_args(h, pol);
+    a.seed_lo = (unsigned)io->seed; a.seed_hi = (unsigned)(io->seed >> 32); a.stream = io->stream;
+    a.z = io->z; a.act = io->actions; a.aidx = io->action_idx; a.probs = io->probs;
+    return launch_policy(h, pol, a, (cudaStream_t)cuda_stream);
+}
+
+int ds_rollout_policy(ds_handle *h, ds_policy *pol, const ds_params *p, const ds_buffers *io, const ds_rollout_io *ro,
+                      const ds_policy_rollout_io *pio, void *cuda_stream)
+{
+    if (!h || !pol || !pio) return fail(DS_ERR_ARG, "ds_rollout_policy: NULL argument");
+    ds::RolloutArgs ra;
+    std::memset(&ra, 0, sizeof ra);
+    if (int rc = fill_step_args(h, p, io, nullptr, true, &ra.s)) return rc;
+    if (int rc = check_policy("ds_rollout_policy", h, pol)) return rc;
+    if (!ro) return fail(DS_ERR_ARG, "ds_rollout_policy: ds_rollout_io is NULL");
+    if (ro->T < 0) return fail(DS_ERR_ARG, "ds_rollout_policy: T < 0");
+    if (ro->actions || ro->action_idx) return fail(DS_ERR_ARG, "ds_rollout_policy: the actions come from the policy; ro->actions / action_idx must be NULL");
+    if (!ro->agg || !ro->done) return fail(DS_ERR_ARG, "ds_rollout_policy: agg/done must be non-NULL");
+    if ((ro->z_tr == nullptr) != (ro->Ni_tr == nullptr))
+        return fail(DS_ERR_ARG, "ds_rollout_policy: z_tr and Ni_tr must be given together");
+    if (ro->T == 0) return DS_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t E = (size_t)h->E, EN = E * h->n, rb = (size_t)h->real_bytes;
+    const size_t zc = (size_t)(h->k + 1) * (h->simplify ? 2 : 5);
+    if (!ro->vel_tr && h->act_stage_bytes < EN * 2 * rb) {          // the step's actions when they are not recorded
+        cudaFree(h->act_stage);
+        h->act_stage = nullptr; h->act_stage_bytes = 0;
+        DS_CUDA(cudaMalloc(&h->act_stage, EN * 2 * rb));
+        h->act_stage_bytes = EN * 2 * rb;
+    }
+    ds::PolicyArgs pa = policy_args(h, pol);
+    pa.seed_lo = (unsigned)pio->seed; pa.seed_hi = (unsigned)(pio->seed >> 32);
+    pa.seed_dev = (const unsigned long long *)pio->seed_dev;
+    pa.z = io->z;
+    ra.s.ctrl = 0; ra.T = 1;
+    ra.agg = ro->agg; ra.done = ro->done;
+    const Geom gm{h->step_blocks, h->step_threads, h->step_smem};
+    auto off = [](void *base, size_t bytes) -> void * { return base ? (void *)((char *)base + bytes) : nullptr; };
+    for (int t = 0; t < ro->T; ++t) {
+        void *act_t = ro->vel_tr ? off(ro->vel_tr, (size_t)t * EN * 2 * rb) : h->act_stage;
+        pa.stream = pio->stream0 + (unsigned)t;
+        pa.act = act_t;
+        pa.aidx = (uint8_t *)off(pio->action_idx_tr, (size_t)t * EN);
+        pa.probs = (float *)off(pio->probs_tr, (size_t)t * EN * pol->A * sizeof(float));
+        if (int rc = launch_policy(h, pol, pa, st)) return rc;
+        ra.actions = act_t;
+        ra.pos_tr = off(ro->pos_tr, (size_t)t * EN * 2 * rb);
+        ra.vel_tr = ro->vel_tr ? act_t : nullptr;            // the kernel rewrites what it has just read
+        ra.r_tr = off(ro->reward_tr, (size_t)t * EN * rb);
+        ra.tr_tr = off(ro->true_reward_tr, (size_t)t * EN * rb);
+        ra.z_tr = off(ro->z_tr, (size_t)t * EN * zc * rb);
+        ra.Ni_tr = (int *)off(ro->Ni_tr, (size_t)t * EN * (h->k + 1) * sizeof(int32_t));
+        ra.ncoll_tr = (int *)off(ro->ncoll_tr, (size_t)t * E * sizeof(int32_t));
+        ra.fin_tr = (uint8_t *)off(ro->finished_tr, (size_t)t * E);
+        if (int rc = launch_rollout_control(h, ra, gm, st)) return rc;
+    }
     return DS_OK;
 }
 

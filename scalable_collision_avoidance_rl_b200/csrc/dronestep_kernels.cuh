@@ -923,9 +923,13 @@ rollout_control_kernel(const RolloutArgs ra)
         __syncthreads();                                   // current positions, alive / t of this step
         const bool alive = active && sm.alive[le] != 0;
         V2 u{};
-        if (alive)
-            control_action<Real>(a.ctrl, n, i, p.x, p.y, c.xF, c.yF, c.ds, c.radius, sm.pos + le * n, sm.radius, 1,
-                                 (Real)a.u_max, u.x, u.y);
+        if (alive) {
+            if (a.ctrl)
+                control_action<Real>(a.ctrl, n, i, p.x, p.y, c.xF, c.yF, c.ds, c.radius, sm.pos + le * n, sm.radius, 1,
+                                     (Real)a.u_max, u.x, u.y);
+            else                                           // actions given (ds_rollout_policy: the actors' draws)
+                u = reinterpret_cast<const V2 *>(ra.actions)[(size_t)step * EN + g];
+        }
         __syncthreads();                                   // everybody has read the old positions
         if (alive) {
             p.x = add_rn(p.x, mul_rn(P.dt, u.x));          // A = I, B = dt I (:78-79,235)

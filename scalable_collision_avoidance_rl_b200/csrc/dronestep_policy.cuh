@@ -43,6 +43,7 @@ constexpr int kPolHeadFloats = kPolHeadB3 + kPolMaxA;          // 5760 floats = 
 struct PolicyArgs {
     int E, n, in_dim, n_actions, real_bytes;
     unsigned seed_lo, seed_hi, stream;
+    const unsigned long long *seed_dev;   // when non-null the seed is read from device memory (graph replays)
     const void *z;            // Real [E][n][in_dim]
     const float *head;        // [n][kPolHeadFloats]
     const float *W2p;         // [n][10 chunks][2 (hi, lo)][8 k-groups][304 rows][4]   operand layout
@@ -298,7 +299,8 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
     for (int q = 0; q < kPolMaxA; ++q) { pr[q] = (q < A) ? expf(logit[q] - mx) : 0.f; sum += pr[q]; }
     if (live) {
         unsigned rnd[4];
-        philox4x32_10((unsigned)e, (unsigned)agent, a.stream, 1u, a.seed_lo, a.seed_hi, rnd);
+        const unsigned long long seed = a.seed_dev ? *a.seed_dev : (((unsigned long long)a.seed_hi << 32) | a.seed_lo);
+        philox4x32_10((unsigned)e, (unsigned)agent, a.stream, 1u, (unsigned)seed, (unsigned)(seed >> 32), rnd);
         const float u = (float)(rnd[0] >> 8) * 5.9604644775390625e-08f;       // [0, 1), 24 bits
         float cdf = 0.f;
         int pick = A - 1;

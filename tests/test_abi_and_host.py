@@ -42,6 +42,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.ds_returns_io) == 2 * 4 + 8 + 7 * 8
     assert ctypes.sizeof(_lib.ds_policy_config) == 6 * 4 + 7 * 8
     assert ctypes.sizeof(_lib.ds_policy_io) == 4 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(_lib.ds_policy_rollout_io) == 2 * 8 + 8 + 8 + 2 * 4
     p = _lib.default_params()
     assert (p.dt, p.collision_weight, p.goal_tol, p.sentinel, p.zero_eps, p.ghost_factor,
             p.max_time_steps) == (0.05, 0.2, 0.2, 9.99e3, -1e-6, 1.1, 200)

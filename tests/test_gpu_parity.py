@@ -644,6 +644,120 @@ def test_policy_forward_vs_fp32_restatement(n, E, k, simplify, A):
     assert np.array_equal(env.pos.cpu().numpy(), p0.cpu().numpy() + 0.05 * tab[idx])
 
 
+@pytest.mark.parametrize("n,E,grid,simplify,A", [(5, 300, [5, 5], True, 8), (10, 129, [5, 5], False, 16)])
+def test_rollout_policy_equals_forward_then_step_and_oracle(n, E, grid, simplify, A):
+    """ds_rollout_policy (the episode loop of train_problem.py:82-104 with the actors on the device)
+    == T x (policy_forward; step) bit for bit on every executed step, with ds_rollout's finished
+    codes / done / episode sums; the open-loop rollout on the recorded indices reproduces it; the
+    C oracle, driven with the recorded actions, agrees on states and rewards (fp64 tolerance)."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    T, k = 70, 2
+    rng = np.random.default_rng(n + A)
+    in_dim = (k + 1) * (2 if simplify else 5)
+    W = _torch_like_weights(rng, n, in_dim, A)
+    W = tuple(w * np.float32(3) if j in (2, 4) else w for j, w in enumerate(W))
+    tab = formation.unit_action_table(A)
+    envs = [BatchedDrones(E, n, grid, "O", k, np.ones(n), simplify, seed=9, warn=False) for _ in range(3)]
+    a, b, c = envs
+    t0 = np.random.default_rng(1).integers(150, 199, E).astype(np.int32)     # episodes end inside the call
+    st, _ = a.get_state()
+    for env in envs:
+        env.load_policy(*W, tab)
+        env.set_state(st, t0)
+        env.observe()
+    rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished", "action_idx", "probs")
+    out = a.rollout_policy(T, seed=11, stream0=100, record=rec)
+    torch.cuda.synchronize()
+    fin_tr = out["finished"].cpu().numpy()
+    idx_tr = out["action_idx"].cpu().numpy()
+    done = np.zeros(E, bool)
+    sums = np.zeros((E, 4))
+    for t in range(T):
+        act, idx, probs = b.policy_forward(seed=11, stream=100 + t)
+        before = (b.pos.clone(), b.vel.clone(), b.internal_t.clone(), b.z_states.clone())
+        (pos, vel), z, r, nc, fin, tr = b.step(act)
+        torch.cuda.synchronize()
+        lv = torch.as_tensor(~done, device=b.device)
+        assert np.array_equal(fin_tr[t][~done], fin.cpu().numpy()[~done]) and (fin_tr[t][done] == 2).all()
+        for key, val in (("pos", pos), ("vel", vel), ("reward", r), ("true_reward", tr), ("z", z), ("Ni", b.Ni),
+                         ("ncoll", nc), ("action_idx", idx), ("probs", probs)):
+            assert torch.equal(out[key][t][lv], val[lv]), f"{key} t={t}"
+        assert torch.equal(out["vel"][t][lv], torch.as_tensor(tab[idx_tr[t]], device=b.device)[lv])
+        live = ~done
+        sums[live, 0] += r.cpu().numpy()[live].mean(1); sums[live, 1] += tr.cpu().numpy()[live].mean(1)
+        sums[live, 2] += nc.cpu().numpy()[live]; sums[live, 3] += 1
+        done |= fin.cpu().numpy().astype(bool) & live
+        dprev = torch.as_tensor(~live, device=b.device)                       # finished before this step: freeze
+        b.pos[dprev] = before[0][dprev]; b.vel[dprev] = before[1][dprev]; b.internal_t[dprev] = before[2][dprev]
+        b.z_states[dprev] = before[3][dprev]
+    assert done.all()
+    assert np.array_equal(out["done"].cpu().numpy().astype(bool), done)
+    assert_close(out["agg"].cpu().numpy(), sums, 1e-9, "episode sums")
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.internal_t, b.internal_t)
+    # open loop on the recorded indices: the time-parallel rollout kernel gives the same episode
+    ref = c.rollout(action_idx=out["action_idx"], action_table=tab, record=("pos", "reward", "true_reward", "ncoll", "finished"))
+    torch.cuda.synchronize()
+    ex = torch.as_tensor(fin_tr != 2, device=a.device)
+    assert torch.equal(ref["finished"], out["finished"])
+    for key in ("pos", "reward", "true_reward", "ncoll"):
+        assert torch.equal(ref[key][ex], out[key][ex]), key
+    # the C oracle on the same actions
+    orc = c_oracle.OracleEnv(E, n, a.end_points, a.d_safety, np.asarray(a.deltas, np.float64).reshape(-1),
+                             a.drone_radius, k, simplify, c_oracle.default_params(a.collision_weight))
+    orc.set_state(st[..., 0:2], st[..., 2:4], t0)
+    executed = fin_tr != 2
+    for t in range(T):
+        res = orc.step(tab[idx_tr[t]].astype(np.float64))
+        m = executed[t]
+        assert_close(out["pos"][t].cpu().numpy()[m], res.pos[m], FP64_TOL, f"oracle pos t={t}")
+        assert_close(out["reward"][t].cpu().numpy()[m], res.r[m], FP64_TOL, f"oracle r t={t}")
+        assert np.array_equal(out["ncoll"][t].cpu().numpy()[m], res.ncoll[m])
+        assert np.array_equal(fin_tr[t][m], res.finished[m].astype(np.uint8))
+
+
+def test_rollout_policy_cuda_graph_replay():
+    """The whole actor-driven episode captured in one CUDA graph; replays with a new device-resident
+    seed give new draws, the same seed reproduces the episode bit for bit."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    n, E, A, T = 5, 64, 8, 20
+    rng = np.random.default_rng(3)
+    W = _torch_like_weights(rng, n, 6, A)
+    tab = formation.unit_action_table(A)
+    env = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=4, warn=False)
+    env.load_policy(*W, tab)
+    st, t0 = env.get_state()
+    seed = torch.tensor([5], dtype=torch.uint64, device=env.device)
+    out = {}
+    rec = ("pos", "reward", "finished", "action_idx")
+
+    def restart():
+        env.set_state(st, t0); env.observe(); env.done.zero_(); env.agg.zero_()
+
+    restart()
+    env.rollout_policy(T, stream0=0, record=rec, out=out, seed_tensor=seed)      # warm-up: attributes, scratch
+    torch.cuda.synchronize()
+    first = {k_: v.clone() for k_, v in out.items()}
+    restart()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            env.rollout_policy(T, stream0=0, record=rec, out=out, seed_tensor=seed)
+    g.replay(); torch.cuda.synchronize()
+    for key in rec:
+        assert torch.equal(out[key], first[key]), key
+    restart()
+    seed.fill_(6)
+    g.replay(); torch.cuda.synchronize()
+    assert not torch.equal(out["action_idx"], first["action_idx"])
+    restart()
+    seed.fill_(5)
+    g.replay(); torch.cuda.synchronize()
+    for key in rec:
+        assert torch.equal(out[key], first[key]), key
+
+
 def test_policy_sampling_statistics():
     """Same observation in 2^15 environments: the sampled indices follow the probabilities
     (chi-square), different streams give different draws, same stream reproduces."""
