@@ -267,6 +267,62 @@ def test_float32_throughput_mode(n, grid, delta):
     assert np.array_equal(ncoll.cpu().numpy(), ref.ncoll)
 
 
+def test_float32_handle_side_paths():
+    """The float32 instantiations of everything around the step (device reset, actors, closed loops,
+    returns): consistent with each other bit for bit, and with the fp64 restatements to fp32
+    accuracy.  float32 is the throughput mode, not the parity path."""
+    from oracle import np_oracle
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    n, E, A, T = 10, 200, 16, 40
+    rng = np.random.default_rng(8)
+    W = _torch_like_weights(rng, n, 6, A)
+    tab = formation.unit_action_table(A)
+    a = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, dtype=torch.float32, seed=1, warn=False)
+    b = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, dtype=torch.float32, seed=1, warn=False)
+    d = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=1, warn=False)          # fp64 twin
+    for env in (a, b, d):
+        env.load_policy(*W, tab)
+        env.reset_random(seed=3, stream=2)
+    torch.cuda.synchronize()
+    assert torch.equal(a.pos, b.pos) and np.array_equal(a.pos.cpu().numpy(), d.pos.cpu().numpy().astype(np.float32))
+    # actors on the f32 observation
+    act, idx, probs = a.policy_forward(seed=2, stream=0)
+    torch.cuda.synchronize()
+    z = a.z_states.cpu().numpy().reshape(E, n, 6)
+    for i in range(n):
+        assert np.abs(probs[:, i].cpu().numpy() - np_oracle.policy_probs(z[:, i], *[w[i] for w in W])).max() <= 1e-5
+    assert act.dtype == torch.float32 and np.array_equal(act.cpu().numpy(), tab.astype(np.float32)[idx.cpu().numpy()])
+    # actor-driven episode == forward; step, and == the open-loop rollout on the recorded indices
+    out = a.rollout_policy(T, seed=2, stream0=0, record=("pos", "reward", "obs", "finished", "action_idx"))
+    for t in range(3):
+        act, idx, _ = b.policy_forward(seed=2, stream=t)
+        (pos, _), zt, r, *_ = b.step(act)
+        torch.cuda.synchronize()
+        assert torch.equal(out["pos"][t], pos) and torch.equal(out["reward"][t], r) and torch.equal(out["z"][t], zt)
+        assert torch.equal(out["action_idx"][t], idx)
+    b.reset_random(seed=3, stream=2)
+    ref = b.rollout(action_idx=out["action_idx"], action_table=tab, record=("pos", "reward", "finished"))
+    torch.cuda.synchronize()
+    assert torch.equal(ref["pos"], out["pos"]) and torch.equal(ref["reward"], out["reward"])
+    # returns in f32 against the fp64 restatement on the same (f32) rewards
+    base = torch.zeros((T, E, n), dtype=torch.float32, device=a.device)
+    ret = a.returns(out["reward"], out["Ni"], out["finished"], discount=0.99, baseline=base)
+    torch.cuda.synchronize()
+    G, adv, cnt = c_oracle.returns(out["reward"].cpu().numpy().astype(np.float64), out["Ni"].cpu().numpy(),
+                                   out["finished"].cpu().numpy(), 0.99, np.zeros((T, E, n)))
+    assert np.abs(ret["returns"].cpu().numpy() - G).max() <= 2e-5 * max(1.0, np.abs(G).max())
+    assert np.array_equal(ret["count"].cpu().numpy(), cnt)
+    # closed loop with the reference's controller: fused == stepped, and close to the fp64 twin
+    a.reset_random(seed=3, stream=5); b.reset_random(seed=3, stream=5); d.reset_random(seed=3, stream=5)
+    fused = a.rollout_control(5, "gradient", record=("pos", "reward"))
+    for t in range(5):
+        (pos, _), _, r, *_ = b.step_control("gradient")
+        (pos64, _), *_ = d.step_control("gradient")
+        torch.cuda.synchronize()
+        assert torch.equal(fused["pos"][t], pos) and torch.equal(fused["reward"][t], r)
+        assert np.abs(pos.cpu().numpy() - pos64.cpu().numpy()).max() < 1e-4
+
+
 def test_full_size_properties():
     """BASELINE config 3 (n = 10, E = 4096) at full size: size-independent invariants."""
     from scalable_collision_avoidance_rl_b200 import BatchedDrones
