@@ -769,7 +769,7 @@ static int launch_policy(ds_handle *h, ds_policy *pol, const ds::PolicyArgs &a, 
     do {                                                                                                \
         DS_CUDA(cudaFuncSetAttribute(ds::policy_kernel<REAL, IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem));                                                       \
-        ds::policy_kernel<REAL, IN><<<grid, 128, smem, st>>>(a);                                        \
+        ds::policy_kernel<REAL, IN><<<grid, ds::kPolThreads, smem, st>>>(a);                                        \
     } while (0)
     const int in_sel = (pol->in_dim == 6) ? 6 : (pol->in_dim == 15 ? 15 : 0);
     if (h->real_bytes == 8) {

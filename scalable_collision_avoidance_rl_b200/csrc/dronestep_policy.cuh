@@ -10,6 +10,8 @@
 // agent), M = E rows each -- and belongs on tcgen05:
 //   * one CTA = one agent x one tile of 128 environments (M = 128 = the TMEM lanes); the W2 chunks
 //     arrive by TMA bulk copies (cp.async.bulk, double buffered, counted on an mbarrier);
+//     warps 0-3 own the 128 rows, one thread of warp 4 issues copies and MMAs (no CTA barrier
+//     in the main loop: mbarrier handshakes both ways);
 //   * layer 1 (K = in_dim, tiny) on the CUDA cores, 16 hidden units at a time, written straight
 //     into shared memory as the A operand of the next layer: K-major, no swizzle, 8 x 16-byte core
 //     matrices (LBO = 128 rows x 16 B between k-groups of 4, SBO = 128 B between 8-row groups);
@@ -84,7 +86,8 @@ struct PolicySmem {
     float W1t[kPolMaxIn][kPolKP];                            // the head block, in ds_policy_create's order (22.5 KB)
     float b1[kPolKP], b2[kPolNP], b3[kPolMaxA];
     float W3t[kPolNP][kPolMaxA];                             // 19 KB
-    unsigned long long full[2], mma_done[2], params;         // mbarriers: W2 chunk landed / MMAs of a half-chunk done / head + W3t landed
+    unsigned long long full[2], mma_done[2], a_ready[2], params;   // mbarriers: W2 chunk landed / MMAs of a half-chunk done /
+                                                             // A half written by the 128 rows / head + W3t landed
     uint32_t tmem_base;
 };
 static_assert(offsetof(PolicySmem, b1) - offsetof(PolicySmem, W1t) == kPolHeadB1 * sizeof(float) &&
@@ -156,25 +159,33 @@ __device__ __forceinline__ void pol_layer3_block(float2 (&lg)[kPolMaxA / 2], con
 // IN = in_dim when it is one of the reference's two observation widths (6: simplify_zstate, 15: full,
 // k = 2), else 0 (any in_dim <= 16, guarded loop).  Layers 1 and 3 run on the packed-f32 pipe
 // (FFMA2: two hidden units / two actions per instruction, operands read as float4).
+// Warp roles: warps 0-3 = one thread per environment row (layer 1, epilogue); warp 4 = one elected
+// thread that issues the bulk copies and the MMAs.  The main loop has no CTA barrier: rows -> issuer
+// through a_ready (128 arrivals), issuer -> rows through tcgen05.commit on mma_done.
+constexpr int kPolThreads = 160;
 template <typename Real, int IN>
-__global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
+__global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(const PolicyArgs a)
 {
     using V2 = typename vec2_of<Real>::type;
     extern __shared__ __align__(128) unsigned char pol_smem_raw[];
     PolicySmem &sm = *reinterpret_cast<PolicySmem *>(pol_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int agent = blockIdx.y;
-    const int e = blockIdx.x * 128 + tid;                    // this thread's environment = TMEM lane tid
-    const bool live = e < a.E;
+    const bool row_thread = tid < 128, issuer = tid == 128;
+    const int e = blockIdx.x * 128 + tid;                    // a row thread's environment = TMEM lane tid
+    const bool live = row_thread && e < a.E;
     const int in_dim = a.in_dim, A = a.n_actions;
 
     // ---- mbarriers, TMEM, and the first copies: parameter block + W3t, W2 chunks 0 and 1
     const float *W2p = a.W2p + (size_t)agent * (kPolKP / kPolChunk) * (kPolChunkBytes / sizeof(float));
-    if (tid == 0) {
+    constexpr int NST = 2 * (kPolKP / kPolChunk);            // 20 half-chunks of 16 hidden units (= 16 of K)
+    if (issuer) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[1])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mma_done[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.mma_done[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pol_smem_u32(&sm.a_ready[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pol_smem_u32(&sm.a_ready[1])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.params)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         pol_expect(&sm.params, kPolHeadBytes + kPolW3tBytes);
@@ -197,45 +208,15 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
-    pol_wait(pol_smem_u32(&sm.params), 0u);
 
-    // ---- layers 1 + 2 in 20 half-chunks of 16 hidden units (= 16 of K).  Step s computes layer 1 into
-    // A half (s & 1) while the MMAs of step s - 1 run from the other half; W2 arrives in chunks of 32
-    // (two steps), the chunk of step s + 4 being copied while steps s + 2, s + 3 compute.
-    constexpr int NST = 2 * (kPolKP / kPolChunk);
-    for (int s_ = 0; s_ < NST; ++s_) {
-        const int ab = s_ & 1, kc = s_ >> 1, bsel = kc & 1;
-        // A half ab was last read by the MMAs of step s - 2
-        if (s_ >= 2) pol_wait(pol_smem_u32(&sm.mma_done[ab]), (uint32_t)((s_ >> 1) - 1) & 1u);
-        // layer 1 for this thread's environment: units 16 s .. 16 s + 15 (utils.py:289-290), split hi / lo
-#pragma unroll
-        for (int kg = 0; kg < 4; ++kg) {
-            const int j0 = s_ * 16 + kg * 4;                                     // units j0 .. j0 + 3 (padding: 0 weights)
-            const float4 bb = *reinterpret_cast<const float4 *>(&sm.b1[j0]);
-            float2 h01 = make_float2(bb.x, bb.y), h23 = make_float2(bb.z, bb.w);
-#pragma unroll
-            for (int d = 0; d < (IN > 0 ? IN : kPolMaxIn); ++d) {
-                if (IN > 0 || d < in_dim) {
-                    const float4 w = *reinterpret_cast<const float4 *>(&sm.W1t[d][j0]);
-                    const float2 zz = make_float2(zin[d], zin[d]);
-                    h01 = __ffma2_rn(make_float2(w.x, w.y), zz, h01);
-                    h23 = __ffma2_rn(make_float2(w.z, w.w), zz, h23);
-                }
-            }
-            const float h[4] = {fmaxf(h01.x, 0.f), fmaxf(h01.y, 0.f), fmaxf(h23.x, 0.f), fmaxf(h23.y, 0.f)};
-            float hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                hi[q] = __uint_as_float(__float_as_uint(h[q]) & 0xffffe000u);    // what kind::tf32 reads
-                lo[q] = h[q] - hi[q];                                            // exact
-            }
-            *reinterpret_cast<float4 *>(&sm.A_hi[ab][kg][tid][0]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4 *>(&sm.A_lo[ab][kg][tid][0]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic stores -> async proxy
-        __syncthreads();
-        if (tid == 0) {
+    if (issuer) {
+        // ---- layer 2: MMAs of step s from A half (s & 1) as soon as the rows have written it.  W2 arrives
+        // in chunks of 32 (two steps); the chunk of step s + 2 is copied into the buffer that the MMAs of
+        // step s - 1 were the last to read.
+        for (int s_ = 0; s_ < NST; ++s_) {
+            const int ab = s_ & 1, kc = s_ >> 1, bsel = kc & 1;
             if (ab == 0) pol_wait(pol_smem_u32(&sm.full[bsel]), (uint32_t)(kc >> 1) & 1u);   // W2 chunk kc has landed
+            pol_wait(pol_smem_u32(&sm.a_ready[ab]), (uint32_t)(s_ >> 1) & 1u);              // A half written, fenced
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {                                     // one MMA = K of 8 = 2 k-groups
@@ -255,18 +236,49 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                 pol_smem_u32(&sm.mma_done[ab])));
-            // the MMAs of step s - 1 (issued a whole layer-1 pass ago) were the last readers of the W2
-            // buffer of chunk kc - 1 when s is even: refill it with chunk kc + 1
             if (ab == 0 && s_ >= 2 && kc + 1 < NST / 2) {
                 pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((s_ - 1) >> 1) & 1u);
                 pol_bulk_load(&sm.B[bsel ^ 1][0][0][0][0], W2p + (size_t)(kc + 1) * (kPolChunkBytes / sizeof(float)),
                               kPolChunkBytes, &sm.full[bsel ^ 1]);
             }
         }
-    }
-    // D may be read once the MMAs of the last step (and with them all earlier ones) are done
-    pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((NST - 1) >> 1) & 1u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else if (row_thread) {
+        pol_wait(pol_smem_u32(&sm.params), 0u);
+        // ---- layer 1 for this thread's environment, 16 units per step (utils.py:289-290), split hi / lo
+        for (int s_ = 0; s_ < NST; ++s_) {
+            const int ab = s_ & 1;
+            // A half ab was last read by the MMAs of step s - 2
+            if (s_ >= 2) pol_wait(pol_smem_u32(&sm.mma_done[ab]), (uint32_t)((s_ >> 1) - 1) & 1u);
+#pragma unroll
+            for (int kg = 0; kg < 4; ++kg) {
+                const int j0 = s_ * 16 + kg * 4;                                 // units j0 .. j0 + 3 (padding: 0 weights)
+                const float4 bb = *reinterpret_cast<const float4 *>(&sm.b1[j0]);
+                float2 h01 = make_float2(bb.x, bb.y), h23 = make_float2(bb.z, bb.w);
+#pragma unroll
+                for (int d = 0; d < (IN > 0 ? IN : kPolMaxIn); ++d) {
+                    if (IN > 0 || d < in_dim) {
+                        const float4 w = *reinterpret_cast<const float4 *>(&sm.W1t[d][j0]);
+                        const float2 zz = make_float2(zin[d], zin[d]);
+                        h01 = __ffma2_rn(make_float2(w.x, w.y), zz, h01);
+                        h23 = __ffma2_rn(make_float2(w.z, w.w), zz, h23);
+                    }
+                }
+                const float h[4] = {fmaxf(h01.x, 0.f), fmaxf(h01.y, 0.f), fmaxf(h23.x, 0.f), fmaxf(h23.y, 0.f)};
+                float hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    hi[q] = __uint_as_float(__float_as_uint(h[q]) & 0xffffe000u);    // what kind::tf32 reads
+                    lo[q] = h[q] - hi[q];                                            // exact
+                }
+                *reinterpret_cast<float4 *>(&sm.A_hi[ab][kg][tid][0]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(&sm.A_lo[ab][kg][tid][0]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic stores -> async proxy
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pol_smem_u32(&sm.a_ready[ab])) : "memory");
+        }
+        // D may be read once the MMAs of the last step (and with them all earlier ones) are done
+        pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((NST - 1) >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: row e of D -> +b2, ReLU -> layer 3 on the CUDA cores; the tcgen05.ld of the next
     // 16 columns is in flight while the current 16 are folded into the logits
@@ -318,6 +330,7 @@ __global__ void __launch_bounds__(128, 1) policy_kernel(const PolicyArgs a)
         reinterpret_cast<V2 *>(a.act)[ga] = reinterpret_cast<const V2 *>(a.atable)[pick];   // action_list[arg] (:309)
         if (a.aidx) a.aidx[ga] = (uint8_t)pick;
     }
+    }   // row threads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
