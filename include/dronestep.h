@@ -289,7 +289,9 @@ typedef struct ds_host_rollout {
     const uint8_t *action_idx;  /* host u8 [T][E][n] */
     const void *action_table;   /* host Real [n_actions][2] */
     void *pos_tr;               /* host, layouts as in ds_rollout_io */
-    void *vel_tr;
+    void *vel_tr;               /* state[:,2:4] = u (drone_env.py:238): written on the host from the
+                                   action stream (all T steps) while the copies drain -- never
+                                   crosses PCIe */
     void *reward_tr;
     void *true_reward_tr;
     void *z_tr;

@@ -12,7 +12,7 @@ SOURCES = [os.path.join(CSRC, "dronestep_abi.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "dronestep_kernels.cuh"), os.path.join(CSRC, "dronestep_policy.cuh"),
                   os.path.join(os.path.dirname(PKG_DIR), "include", "dronestep.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC,-pthread", "-shared", "-cudart", "shared"]
 
 
 def needs_build() -> bool:

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -911,7 +912,8 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
     size_t out_step = 0;
     unsigned mask = index_mode ? 1u : 0u;
     if (hr->pos_tr) { out_step += A * 2 * rb; mask |= 2u; }
-    if (hr->vel_tr) { out_step += A * 2 * rb; mask |= 4u; }
+    // state[:,2:4] = u (drone_env.py:238): the recorded velocity IS the action the host has just
+    // supplied, so it is written on the host while the pipeline drains and never crosses PCIe
     if (hr->reward_tr) { out_step += A * rb; mask |= 8u; }
     if (hr->true_reward_tr) { out_step += A * rb; mask |= 16u; }
     if (hr->z_tr) { out_step += A * zc * rb + A * (h->k + 1) * 4; mask |= 32u; }
@@ -942,7 +944,6 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
             const size_t c = chunk;
             if (index_mode) DS_CUDA(cudaMalloc(&s.aidx, c * A)); else DS_CUDA(cudaMalloc(&s.act, c * A * 2 * rb));
             if (hr->pos_tr) DS_CUDA(cudaMalloc(&s.pos, c * A * 2 * rb));
-            if (hr->vel_tr) DS_CUDA(cudaMalloc(&s.vel, c * A * 2 * rb));
             if (hr->reward_tr) DS_CUDA(cudaMalloc(&s.r, c * A * rb));
             if (hr->true_reward_tr) DS_CUDA(cudaMalloc(&s.tr, c * A * rb));
             if (hr->z_tr) {
@@ -987,7 +988,7 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
         ro.T = tc; ro.n_actions = hr->n_actions;
         ro.actions = index_mode ? nullptr : s.act;
         ro.action_idx = s.aidx; ro.action_table = h->d_atable;
-        ro.pos_tr = s.pos; ro.vel_tr = s.vel; ro.reward_tr = s.r; ro.true_reward_tr = s.tr;
+        ro.pos_tr = s.pos; ro.vel_tr = nullptr; ro.reward_tr = s.r; ro.true_reward_tr = s.tr;
         ro.z_tr = s.z; ro.Ni_tr = s.Ni; ro.ncoll_tr = s.ncoll; ro.finished_tr = s.fin;
         ro.agg = h->d_agg; ro.done = h->d_done;
         if (int rc = ds_rollout(h, p, io, &ro, cuda_stream)) return rc;
@@ -996,7 +997,6 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
         DS_CUDA(cudaStreamWaitEvent(h->s_d2h, s.kernel_done, 0));
         cudaStream_t d = h->s_d2h;
         if (hr->pos_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->pos_tr + t0s * A * 2 * rb, s.pos, tcs * A * 2 * rb, cudaMemcpyDeviceToHost, d));
-        if (hr->vel_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->vel_tr + t0s * A * 2 * rb, s.vel, tcs * A * 2 * rb, cudaMemcpyDeviceToHost, d));
         if (hr->reward_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->reward_tr + t0s * A * rb, s.r, tcs * A * rb, cudaMemcpyDeviceToHost, d));
         if (hr->true_reward_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->true_reward_tr + t0s * A * rb, s.tr, tcs * A * rb, cudaMemcpyDeviceToHost, d));
         if (hr->z_tr) {
@@ -1009,6 +1009,26 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
     }
     if (hr->agg)
         DS_CUDA(cudaMemcpyAsync(hr->agg, h->d_agg, E * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (hr->vel_tr && hr->T > 0) {
+        // everything is enqueued; this thread would only wait.  A few host threads write vel_tr = u.
+        const size_t total = (size_t)hr->T * A;                       // (step, environment, agent) rows
+        const int nth = (int)std::min<size_t>(4, std::max<size_t>(1, total >> 16));
+        auto fill = [&](size_t lo, size_t hi) {
+            if (!index_mode) {
+                std::memcpy((char *)hr->vel_tr + lo * 2 * rb, (const char *)hr->actions + lo * 2 * rb, (hi - lo) * 2 * rb);
+            } else if (rb == 8) {
+                const double *tab = (const double *)hr->action_table; double *o = (double *)hr->vel_tr;
+                for (size_t q = lo; q < hi; ++q) { const unsigned a = hr->action_idx[q]; o[2 * q] = tab[2 * a]; o[2 * q + 1] = tab[2 * a + 1]; }
+            } else {
+                const float *tab = (const float *)hr->action_table; float *o = (float *)hr->vel_tr;
+                for (size_t q = lo; q < hi; ++q) { const unsigned a = hr->action_idx[q]; o[2 * q] = tab[2 * a]; o[2 * q + 1] = tab[2 * a + 1]; }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < nth; ++w) pool.emplace_back(fill, total * w / nth, total * (w + 1) / nth);
+        fill(0, total / nth);
+        for (auto &t : pool) t.join();
+    }
     DS_CUDA(cudaStreamSynchronize(st));
     DS_CUDA(cudaStreamSynchronize(h->s_d2h));
     DS_CUDA(cudaStreamSynchronize(h->s_h2d));
