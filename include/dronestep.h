@@ -272,6 +272,14 @@ typedef struct ds_host_step_out {
 int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p,
                  const ds_buffers *io, const ds_host_step_out *out, void *cuda_stream);
 
+/* The same step when the caller has laid out io's result buffers inside ONE device allocation
+ * [dev_block, dev_block + bytes): actions up, ds_step, a single device->host transfer of the
+ * whole block into host_block (same layout), one synchronise.  For the one-environment drop-in
+ * class the eight separate copies of ds_step_host are most of the call's latency.  Every
+ * non-NULL result pointer of io must lie inside the block. */
+int ds_step_host_block(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,
+                       const void *dev_block, void *host_block, size_t bytes, void *cuda_stream);
+
 /* T fused steps with a HOST action stream and HOST trajectory buffers (Real of
  * the handle's precision; pinned memory recommended) -- the end-to-end form of
  * the episode loop (train_problem.py:82-107): everything the loop's host side

@@ -71,14 +71,29 @@ class BatchedDrones:
 
         E, n, k = self.n_envs, self.n_agents, self.k_closest
         dev, dt_ = self.device, self.dtype
-        self.pos = torch.zeros((E, n, 2), dtype=dt_, device=dev)
-        self.vel = torch.zeros((E, n, 2), dtype=dt_, device=dev)
-        self.rewards = torch.zeros((E, n), dtype=dt_, device=dev)
-        self.true_rewards = torch.zeros((E, n), dtype=dt_, device=dev)
-        self.z_states = torch.zeros((E, n, k + 1, self.cols), dtype=dt_, device=dev)
-        self.Ni = torch.full((E, n, k + 1), -1, dtype=torch.int32, device=dev)
-        self.n_collisions = torch.zeros(E, dtype=torch.int32, device=dev)
-        self.finished = torch.zeros(E, dtype=torch.uint8, device=dev)
+        # the step's state and results live in ONE device allocation (256-byte aligned pieces), so
+        # that step_host() brings the whole 6-tuple back in a single transfer (ds_step_host_block)
+        self._layout, off = {}, 0
+        for name, shape, dtype in (("pos", (E, n, 2), dt_), ("vel", (E, n, 2), dt_),
+                                   ("z", (E, n, k + 1, self.cols), dt_), ("r", (E, n), dt_), ("tr", (E, n), dt_),
+                                   ("Ni", (E, n, k + 1), torch.int32), ("nc", (E,), torch.int32),
+                                   ("fin", (E,), torch.uint8)):
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            self._layout[name] = (off, nbytes, shape, dtype)
+            off += (nbytes + 255) // 256 * 256
+        self._block = torch.zeros(off, dtype=torch.uint8, device=dev)
+        self._hblock = None
+
+        def piece(block, name):
+            o, nb, shape, dtype = self._layout[name]
+            return block[o:o + nb].view(dtype).view(shape)
+
+        self._piece = piece
+        self.pos, self.vel = piece(self._block, "pos"), piece(self._block, "vel")
+        self.rewards, self.true_rewards = piece(self._block, "r"), piece(self._block, "tr")
+        self.z_states = piece(self._block, "z")
+        self.Ni = piece(self._block, "Ni"); self.Ni.fill_(-1)
+        self.n_collisions, self.finished = piece(self._block, "nc"), piece(self._block, "fin")
         self.internal_t = torch.zeros(E, dtype=torch.int32, device=dev)
         self.done = torch.zeros(E, dtype=torch.uint8, device=dev)
         self.agg = torch.zeros((E, 4), dtype=torch.float64, device=dev)
@@ -218,24 +233,31 @@ class BatchedDrones:
         return ((self.pos, self.vel), self.z_states, self.rewards, self.n_collisions, self.finished,
                 self.true_rewards)
 
-    def step_host(self, actions):
-        """Same step with HOST arrays in and out (ds_step_host): one H2D, one kernel, D2H of the
-        reference's 6-tuple into pinned buffers, one synchronise.  Returns numpy views."""
+    def step_host(self, actions, block=True):
+        """Same step with HOST arrays in and out: one H2D, one kernel, the reference's 6-tuple back
+        into pinned memory, one synchronise.  block=True (ds_step_host_block): ONE D2H of the whole
+        result block; block=False (ds_step_host): one copy per array.  Returns numpy views (keys
+        pos, vel, z, r, tr, Ni, nc, fin) that the next call overwrites."""
         E, n, k = self.n_envs, self.n_agents, self.k_closest
         a = self._pin("act", (E, n, 2), self.dtype)
         a.numpy()[...] = np.asarray(actions).reshape(E, n, 2)
-        o = dict(pos=self._pin("pos", (E, n, 2), self.dtype), vel=self._pin("vel", (E, n, 2), self.dtype),
-                 z=self._pin("z", (E, n, k + 1, self.cols), self.dtype),
-                 r=self._pin("r", (E, n), self.dtype), tr=self._pin("tr", (E, n), self.dtype),
-                 Ni=self._pin("Ni", (E, n, k + 1), torch.int32), nc=self._pin("nc", (E,), torch.int32),
-                 fin=self._pin("fin", (E,), torch.uint8))
-        out = _lib.ds_host_step_out(o["pos"].data_ptr(), o["vel"].data_ptr(), o["z"].data_ptr(),
-                                    o["r"].data_ptr(), o["tr"].data_ptr(), o["Ni"].data_ptr(),
-                                    o["nc"].data_ptr(), o["fin"].data_ptr())
         p = self._params()
-        _lib.check(self.lib.ds_step_host(self._h, _ptr(a), ctypes.byref(p), ctypes.byref(self._io),
-                                         ctypes.byref(out), self._stream()), "ds_step_host")
-        return {k_: v.numpy() for k_, v in o.items()}
+        if not block:
+            o = {name: self._pin(name, shape, dtype) for name, (_, _, shape, dtype) in self._layout.items()}
+            out = _lib.ds_host_step_out(o["pos"].data_ptr(), o["vel"].data_ptr(), o["z"].data_ptr(),
+                                        o["r"].data_ptr(), o["tr"].data_ptr(), o["Ni"].data_ptr(),
+                                        o["nc"].data_ptr(), o["fin"].data_ptr())
+            _lib.check(self.lib.ds_step_host(self._h, _ptr(a), ctypes.byref(p), ctypes.byref(self._io),
+                                             ctypes.byref(out), self._stream()), "ds_step_host")
+            return {k_: v.numpy() for k_, v in o.items()}
+        if self._hblock is None:
+            self._hblock = torch.empty(self._block.numel(), dtype=torch.uint8, pin_memory=True)
+            self._hviews = {name: self._piece(self._hblock, name).numpy() for name in self._layout}
+        _lib.check(self.lib.ds_step_host_block(self._h, _ptr(a), ctypes.byref(p), ctypes.byref(self._io),
+                                               _ptr(self._block), _ptr(self._hblock),
+                                               ctypes.c_size_t(self._block.numel()), self._stream()),
+                   "ds_step_host_block")
+        return self._hviews
 
     # ------------------------------------------------------------------ rollout
     def rollout(self, actions=None, action_idx=None, action_table=None, record=("reward", "true_reward",

@@ -892,6 +892,32 @@ int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p, con
     return DS_OK;
 }
 
+int ds_step_host_block(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,
+                       const void *dev_block, void *host_block, size_t bytes, void *cuda_stream)
+{
+    if (!h || !actions_host || !io || !dev_block || !host_block)
+        return fail(DS_ERR_ARG, "ds_step_host_block: NULL argument");
+    const char *lo = (const char *)dev_block, *hi = lo + bytes;
+    const void *ptrs[] = {io->pos, io->vel, io->reward, io->true_reward, io->z, io->Ni, io->ncoll, io->finished};
+    for (const void *q : ptrs)
+        if (q && ((const char *)q < lo || (const char *)q >= hi))
+            return fail(DS_ERR_ARG, "ds_step_host_block: a result buffer of io lies outside the block");
+    DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t act_bytes = (size_t)h->E * h->n * 2 * h->real_bytes;
+    if (h->act_stage_bytes < act_bytes) {
+        cudaFree(h->act_stage);
+        h->act_stage = nullptr; h->act_stage_bytes = 0;
+        DS_CUDA(cudaMalloc(&h->act_stage, act_bytes));
+        h->act_stage_bytes = act_bytes;
+    }
+    DS_CUDA(cudaMemcpyAsync(h->act_stage, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
+    if (int rc = ds_step(h, h->act_stage, p, io, cuda_stream)) return rc;
+    DS_CUDA(cudaMemcpyAsync(host_block, dev_block, bytes, cudaMemcpyDeviceToHost, st));
+    DS_CUDA(cudaStreamSynchronize(st));
+    return DS_OK;
+}
+
 int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_host_rollout *hr,
                     void *cuda_stream)
 {

@@ -137,6 +137,7 @@ class drones:
     def rewards(self, state, end_points, n_agents, d_safety, deltas):
         """Fused distance/reward/observation evaluation of `state` (drone_env.py:260-293)."""
         eng = self._engine(end_points, d_safety, deltas)
+        self._synced = None                              # the device state is overwritten below
         eng.set_state(np.asarray(state, np.float64)[None], internal_t=self.internal_t)
         eng.observe()
         r = eng.rewards[0].cpu().numpy()
@@ -154,8 +155,12 @@ class drones:
         for i in range(n):
             act[i] = np.asarray(actions[i], np.float64).reshape(-1)[:dim]
         eng = self._engine(self.end_points, self.d_safety, self.deltas)
-        # the host array is the source of truth (callers may have edited it in place)
-        eng.set_state(self.state[None], internal_t=self.internal_t)
+        # the host array is the source of truth (callers may have edited it in place): upload it unless
+        # it still is, bit for bit, what the device left after the previous step
+        sync = getattr(self, "_synced", None)
+        if not (sync is not None and sync[0] is eng and sync[2] == self.internal_t
+                and sync[1].shape == self.state.shape and np.array_equal(sync[1], self.state, equal_nan=True)):
+            eng.set_state(self.state[None], internal_t=self.internal_t)
         out = eng.step_host(act[None])
         self.state[:, 0:dim] = out["pos"][0]
         self.state[:, dim:2 * dim] = out["vel"][0]
@@ -164,6 +169,7 @@ class drones:
         self.Ni = Ni
         finished = bool(out["fin"][0])
         self.internal_t += 1
+        self._synced = (eng, self.state.copy(), self.internal_t)
         return (self.state, z_states, np.array(out["r"][0]), np.int64(out["nc"][0]), finished,
                 np.array(out["tr"][0]))
 

@@ -230,6 +230,11 @@ def test_host_entries_match_device_entries():
     assert np.array_equal(o["pos"], a.pos.cpu().numpy()) and np.array_equal(o["r"], a.rewards.cpu().numpy())
     assert np.array_equal(o["z"], a.z_states.cpu().numpy()) and np.array_equal(o["Ni"], a.Ni.cpu().numpy())
     assert np.array_equal(o["nc"], a.n_collisions.cpu().numpy())
+    # one transfer of the result block (ds_step_host_block) == one copy per array (ds_step_host)
+    c = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    o2 = c.step_host(act[0], block=False)
+    for key in ("pos", "vel", "z", "r", "tr", "Ni", "nc", "fin"):
+        assert np.array_equal(o[key], o2[key]), key
     rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
     da = a.rollout(actions=torch.as_tensor(act[1:], device=a.device), record=rec)
     for chunk in (0, 5, 36, 100):
