@@ -355,12 +355,15 @@ def run_ours(args, wl):
         zc = (K_CLOSEST + 1) * 2
         e2e = {"value": world * E * n * e2e_steps / float(el.item()), "unit": "agent-steps/s",
                "h2d_bytes_per_step": A * 2 * rb,
-               # pos, r, true_r, z, Ni, ncoll, finished; vel (= the action, drone_env.py:238) is written on
-               # the host from the action stream by ds_rollout_host and does not cross PCIe
+               # pos, r, true_r, z, Ni, ncoll, finished; vel (= the action, drone_env.py:238) is returned
+               # as a view of the host action stream and does not cross PCIe
                "d2h_bytes_per_step": A * (2 * rb + rb + rb + zc * rb + 4 * (K_CLOSEST + 1)) + E * 5,
                "steps": e2e_steps,
                "api": "BatchedDrones.rollout_host -> ds_rollout_host (pinned host buffers, "
-                      "H2D/D2H pipelined against the kernel)"}
+                      "H2D/D2H pipelined against the kernel)",
+               "note": "state, observations, rewards, neighbour lists, collision counts and finished flags of "
+                       "every step come back; the velocity columns equal the supplied actions "
+                       "(drone_env.py:238) and are returned as a view of the host action stream"}
 
     if rank != 0:
         if world > 1:

@@ -299,7 +299,7 @@ typedef struct ds_host_rollout {
     void *pos_tr;               /* host, layouts as in ds_rollout_io */
     void *vel_tr;               /* state[:,2:4] = u (drone_env.py:238): written on the host from the
                                    action stream (all T steps) while the copies drain -- never
-                                   crosses PCIe */
+                                   crosses PCIe; vel_tr == actions (alias) costs nothing */
     void *reward_tr;
     void *true_reward_tr;
     void *z_tr;

@@ -357,7 +357,8 @@ class BatchedDrones:
                      chunk=0, out=None):
         """End-to-end episode loop with HOST buffers (ds_rollout_host): pinned host action stream
         in, pinned host trajectories out, copies pipelined against the kernel.  `actions` /
-        `action_idx` must be pinned CPU tensors (or are copied into pinned staging)."""
+        `action_idx` must be pinned CPU tensors (or are copied into pinned staging).  out["vel"]
+        is a view of the action stream when explicit actions are given."""
         E, n, k = self.n_envs, self.n_agents, self.k_closest
         hr = _lib.ds_host_rollout()
         keep = []
@@ -390,7 +391,13 @@ class BatchedDrones:
 
         dt_ = self.dtype
         if "pos" in rec: hr.pos_tr = hbuf("pos", (T, E, n, 2), dt_)
-        if "vel" in rec: hr.vel_tr = hbuf("vel", (T, E, n, 2), dt_)
+        if "vel" in rec:
+            # state[:,2:4] = u (drone_env.py:238): with explicit actions the recorded velocity IS the
+            # action stream -- returned as a view of it, nothing copied; index mode: table[idx] on the host
+            if actions is not None:
+                out["vel"] = keep[0].view(T, E, n, 2); hr.vel_tr = hr.actions
+            else:
+                hr.vel_tr = hbuf("vel", (T, E, n, 2), dt_)
         if "reward" in rec: hr.reward_tr = hbuf("reward", (T, E, n), dt_)
         if "true_reward" in rec: hr.true_reward_tr = hbuf("true_reward", (T, E, n), dt_)
         if "obs" in rec:

@@ -1035,7 +1035,7 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
     }
     if (hr->agg)
         DS_CUDA(cudaMemcpyAsync(hr->agg, h->d_agg, E * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (hr->vel_tr && hr->T > 0) {
+    if (hr->vel_tr && hr->vel_tr != hr->actions && hr->T > 0) {      // vel_tr == actions: the caller aliases them
         // everything is enqueued; this thread would only wait.  A few host threads write vel_tr = u.
         const size_t total = (size_t)hr->T * A;                       // (step, environment, agent) rows
         const int nth = (int)std::min<size_t>(4, std::max<size_t>(1, total >> 16));

@@ -246,6 +246,18 @@ def test_host_entries_match_device_entries():
             assert torch.equal(hb[key], da[key].cpu()), f"{key} chunk={chunk}"
         # episode sums are reduced per call (rows first, then agents): chunking only reorders additions
         assert_close(hb["agg"].numpy(), da["agg"].cpu().numpy(), FP64_TOL, f"agg chunk={chunk}")
+    # index mode: u8 indices + table in; the recorded velocity is table[idx], written on the host
+    from scalable_collision_avoidance_rl_b200 import formation
+    tab = formation.unit_action_table(16)
+    idx = rng.integers(0, 16, (T, E, n)).astype(np.uint8)
+    c1 = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    c2 = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    dd = c1.rollout(action_idx=torch.as_tensor(idx, device=c1.device), action_table=tab, record=rec)
+    hh = c2.rollout_host(action_idx=idx, action_table=tab, record=rec, chunk=7)
+    torch.cuda.synchronize()
+    for key in ("pos", "vel", "reward", "true_reward", "z", "Ni", "ncoll", "finished"):
+        assert torch.equal(hh[key], dd[key].cpu()), f"index mode {key}"
+    assert np.array_equal(hh["vel"].numpy(), tab[idx])
 
 
 @pytest.mark.parametrize("n,grid,delta", [(10, [5, 5], 1.0), (32, [32, 32], 2.5)])
