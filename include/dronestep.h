@@ -48,6 +48,7 @@ extern "C" {
 #define DS_ERR_ARG (-1)         /* bad argument / unsupported shape */
 #define DS_ERR_CUDA (-2)        /* CUDA runtime error */
 #define DS_ERR_NO_DEVICE (-3)   /* no CUDA device: the library has no CPU path */
+#define DS_ERR_INTERNAL (-4)    /* host-side exception (out of memory, thread creation): caught, never thrown across */
 
 #define DS_MAX_AGENTS 1024
 #define DS_MAX_K 16

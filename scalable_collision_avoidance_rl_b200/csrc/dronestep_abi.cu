@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -59,7 +60,7 @@ struct ds_handle {
     // ds_rollout_host: two staging slots, two copy streams, events
     struct Slot {
         void *act = nullptr; uint8_t *aidx = nullptr;
-        void *pos = nullptr, *vel = nullptr, *r = nullptr, *tr = nullptr, *z = nullptr;
+        void *pos = nullptr, *r = nullptr, *tr = nullptr, *z = nullptr;
         int32_t *Ni = nullptr, *ncoll = nullptr; uint8_t *fin = nullptr;
         cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
     } slot[2];
@@ -307,7 +308,7 @@ int launch_rollout(ds_handle *h, const ds::RolloutArgs &a, cudaStream_t st)
 void free_slots(ds_handle *h)
 {
     for (auto &s : h->slot) {
-        cudaFree(s.act); cudaFree(s.aidx); cudaFree(s.pos); cudaFree(s.vel); cudaFree(s.r);
+        cudaFree(s.act); cudaFree(s.aidx); cudaFree(s.pos); cudaFree(s.r);
         cudaFree(s.tr); cudaFree(s.z); cudaFree(s.Ni); cudaFree(s.ncoll); cudaFree(s.fin);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.kernel_done) cudaEventDestroy(s.kernel_done);
@@ -357,7 +358,7 @@ void ds_default_params(ds_params *p)
 }
 
 int ds_create(const ds_config *cfg, ds_handle **out)
-{
+try {
     if (!cfg || !out) return fail(DS_ERR_ARG, "ds_create: NULL argument");
     *out = nullptr;
     if (cfg->n_envs < 1) return fail(DS_ERR_ARG, "ds_create: n_envs < 1");
@@ -401,6 +402,10 @@ int ds_create(const ds_config *cfg, ds_handle **out)
     if (rc != DS_OK) { ds_destroy(h); return rc; }
     *out = h;
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_create: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_create: unknown host exception");
 }
 
 void ds_destroy(ds_handle *h)
@@ -419,17 +424,21 @@ void ds_destroy(ds_handle *h)
 
 int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p, const ds_buffers *io,
             void *cuda_stream)
-{
+try {
     ds::StepArgs a;
     if (int rc = fill_step_args(h, p, io, actions_dev, true, &a)) return rc;
     if (!actions_dev) return fail(DS_ERR_ARG, "ds_step: actions_dev is NULL");
     DeviceGuard guard(h->device);
     return launch_step(h, a, (cudaStream_t)cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_step: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_step: unknown host exception");
 }
 
 int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params *p, const ds_buffers *io,
                     void *cuda_stream)
-{
+try {
     ds::StepArgs a;
     if (int rc = fill_step_args(h, p, io, nullptr, true, &a)) return rc;
     if (controller != DS_CTRL_PROPORTIONAL && controller != DS_CTRL_GRADIENT)
@@ -438,6 +447,10 @@ int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params 
     a.ctrl = controller; a.u_max = u_max;
     DeviceGuard guard(h->device);
     return launch_step(h, a, (cudaStream_t)cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_step_control: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_step_control: unknown host exception");
 }
 
 static int launch_rollout_control(ds_handle *h, const ds::RolloutArgs &ra, const Geom &gm, cudaStream_t st)
@@ -448,7 +461,7 @@ static int launch_rollout_control(ds_handle *h, const ds::RolloutArgs &ra, const
 
 int ds_rollout_control(ds_handle *h, int controller, double u_max, const ds_params *p, const ds_buffers *io,
                        const ds_rollout_io *ro, void *cuda_stream)
-{
+try {
     ds::RolloutArgs ra;
     std::memset(&ra, 0, sizeof ra);
     if (int rc = fill_step_args(h, p, io, nullptr, true, &ra.s)) return rc;
@@ -470,19 +483,27 @@ int ds_rollout_control(ds_handle *h, int controller, double u_max, const ds_para
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const Geom gm{h->step_blocks, h->step_threads, h->step_smem};
     return launch_rollout_control(h, ra, gm, st);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_rollout_control: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_rollout_control: unknown host exception");
 }
 
 int ds_observe(ds_handle *h, const ds_params *p, const ds_buffers *io, void *cuda_stream)
-{
+try {
     ds::StepArgs a;
     if (int rc = fill_step_args(h, p, io, nullptr, false, &a)) return rc;
     DeviceGuard guard(h->device);
     return launch_step(h, a, (cudaStream_t)cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_observe: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_observe: unknown host exception");
 }
 
 int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_rollout_io *ro,
                void *cuda_stream)
-{
+try {
     ds::RolloutArgs ra;
     if (int rc = fill_step_args(h, p, io, nullptr, true, &ra.s)) return rc;
     if (!ro) return fail(DS_ERR_ARG, "ds_rollout: ds_rollout_io is NULL");
@@ -522,19 +543,27 @@ int ds_rollout(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_
         if (int rc = launch_rollout(h, ra, (cudaStream_t)cuda_stream)) return rc;
     }
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_rollout: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_rollout: unknown host exception");
 }
 
 int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, void *cuda_stream)
-{
+try {
     if (!h || !agg_dev || !out_dev) return fail(DS_ERR_ARG, "ds_reduce_aggregates: NULL argument");
     DeviceGuard guard(h->device);
     ds::reduce_agg_kernel<<<1, 1024, 0, (cudaStream_t)cuda_stream>>>(agg_dev, h->E, out_dev);
     DS_CUDA(cudaGetLastError());
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_reduce_aggregates: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_reduce_aggregates: unknown host exception");
 }
 
 int ds_returns(ds_handle *h, const ds_returns_io *io, void *cuda_stream)
-{
+try {
     if (!h || !io) return fail(DS_ERR_ARG, "ds_returns: NULL argument");
     if (io->T < 0) return fail(DS_ERR_ARG, "ds_returns: T < 0");
     if (!io->reward_tr || !io->Ni_tr || !io->finished_tr || !io->returns || !io->advantage)
@@ -565,11 +594,15 @@ int ds_returns(ds_handle *h, const ds_returns_io *io, void *cuda_stream)
     }
     DS_CUDA(cudaGetLastError());
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_returns: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_returns: unknown host exception");
 }
 
 int ds_set_state(ds_handle *h, const double *state_host, const int32_t *t_host, const ds_buffers *io,
                  void *cuda_stream)
-{
+try {
     if (!h || !state_host || !io || !io->pos || !io->vel)
         return fail(DS_ERR_ARG, "ds_set_state: NULL argument");
     DeviceGuard guard(h->device);
@@ -593,11 +626,15 @@ int ds_set_state(ds_handle *h, const double *state_host, const int32_t *t_host, 
         DS_CUDA(cudaMemcpyAsync(io->t, t_host, sizeof(int32_t) * h->E, cudaMemcpyHostToDevice, st));
     DS_CUDA(cudaStreamSynchronize(st));
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_set_state: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_set_state: unknown host exception");
 }
 
 int ds_get_state(ds_handle *h, double *state_host, int32_t *t_host, const ds_buffers *io,
                  void *cuda_stream)
-{
+try {
     if (!h || !state_host || !io || !io->pos || !io->vel)
         return fail(DS_ERR_ARG, "ds_get_state: NULL argument");
     DeviceGuard guard(h->device);
@@ -622,11 +659,15 @@ int ds_get_state(ds_handle *h, double *state_host, int32_t *t_host, const ds_buf
         row[4] = h->h_radius[a % h->n];
     }
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_get_state: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_get_state: unknown host exception");
 }
 
 int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p, const ds_buffers *io,
              void *cuda_stream)
-{
+try {
     if (!h || !pos_host || !io || !io->pos || !io->vel)
         return fail(DS_ERR_ARG, "ds_reset: NULL argument");
     DeviceGuard guard(h->device);
@@ -646,11 +687,15 @@ int ds_reset(ds_handle *h, const double *pos_host, const ds_params *p, const ds_
     if (io->finished) DS_CUDA(cudaMemsetAsync(io->finished, 0, h->E, st));
     DS_CUDA(cudaStreamSynchronize(st));   // tmp must outlive the copy
     return ds_observe(h, p, io, cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_reset: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_reset: unknown host exception");
 }
 
 int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, int32_t d1, double pitch,
                     const ds_params *p, const ds_buffers *io, void *cuda_stream)
-{
+try {
     if (!h || !io || !io->pos || !io->vel) return fail(DS_ERR_ARG, "ds_reset_random: NULL argument");
     if (d0 < 1 || d1 < 1 || (long long)d0 * d1 > 0x7fffffffLL)
         return fail(DS_ERR_ARG, "ds_reset_random: bad lattice shape");
@@ -670,6 +715,10 @@ int ds_reset_random(ds_handle *h, uint64_t seed, uint32_t stream, int32_t d0, in
     else ds::reset_random_kernel<float><<<blocks, threads, smem, st>>>(a);
     DS_CUDA(cudaGetLastError());
     return ds_observe(h, p, io, cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_reset_random: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_reset_random: unknown host exception");
 }
 
 struct ds_policy {
@@ -679,7 +728,7 @@ struct ds_policy {
 };
 
 int ds_policy_create(const ds_policy_config *cfg, ds_policy **out)
-{
+try {
     if (!cfg || !out) return fail(DS_ERR_ARG, "ds_policy_create: NULL argument");
     *out = nullptr;
     if (cfg->n_agents < 1 || cfg->in_dim < 1 || cfg->in_dim > ds::kPolMaxIn || cfg->n_actions < 1 ||
@@ -742,6 +791,10 @@ int ds_policy_create(const ds_policy_config *cfg, ds_policy **out)
     if (e != cudaSuccess) { ds_policy_destroy(p); return fail(DS_ERR_CUDA, std::string("ds_policy_create: ") + cudaGetErrorString(e)); }
     *out = p;
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_policy_create: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_policy_create: unknown host exception");
 }
 
 void ds_policy_destroy(ds_policy *p)
@@ -795,7 +848,7 @@ static ds::PolicyArgs policy_args(ds_handle *h, ds_policy *pol)
 }
 
 int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void *cuda_stream)
-{
+try {
     if (!h || !pol || !io || !io->z || !io->actions) return fail(DS_ERR_ARG, "ds_policy_forward: NULL argument");
     if (int rc = check_policy("ds_policy_forward", h, pol)) return rc;
     DeviceGuard guard(h->device);
@@ -803,11 +856,15 @@ int ds_policy_forward(ds_handle *h, ds_policy *pol, const ds_policy_io *io, void
     a.seed_lo = (unsigned)io->seed; a.seed_hi = (unsigned)(io->seed >> 32); a.stream = io->stream;
     a.z = io->z; a.act = io->actions; a.aidx = io->action_idx; a.probs = io->probs;
     return launch_policy(h, pol, a, (cudaStream_t)cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_policy_forward: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_policy_forward: unknown host exception");
 }
 
 int ds_rollout_policy(ds_handle *h, ds_policy *pol, const ds_params *p, const ds_buffers *io, const ds_rollout_io *ro,
                       const ds_policy_rollout_io *pio, void *cuda_stream)
-{
+try {
     if (!h || !pol || !pio) return fail(DS_ERR_ARG, "ds_rollout_policy: NULL argument");
     ds::RolloutArgs ra;
     std::memset(&ra, 0, sizeof ra);
@@ -857,11 +914,15 @@ int ds_rollout_policy(ds_handle *h, ds_policy *pol, const ds_params *p, const ds
         if (int rc = launch_rollout_control(h, ra, gm, st)) return rc;
     }
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_rollout_policy: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_rollout_policy: unknown host exception");
 }
 
 int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,
                  const ds_host_step_out *out, void *cuda_stream)
-{
+try {
     if (!h || !actions_host || !out) return fail(DS_ERR_ARG, "ds_step_host: NULL argument");
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -890,11 +951,15 @@ int ds_step_host(ds_handle *h, const void *actions_host, const ds_params *p, con
     if (out->finished) DS_CUDA(cudaMemcpyAsync(out->finished, io->finished, h->E, cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_step_host: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_step_host: unknown host exception");
 }
 
 int ds_step_host_block(ds_handle *h, const void *actions_host, const ds_params *p, const ds_buffers *io,
                        const void *dev_block, void *host_block, size_t bytes, void *cuda_stream)
-{
+try {
     if (!h || !actions_host || !io || !dev_block || !host_block)
         return fail(DS_ERR_ARG, "ds_step_host_block: NULL argument");
     const char *lo = (const char *)dev_block, *hi = lo + bytes;
@@ -916,11 +981,15 @@ int ds_step_host_block(ds_handle *h, const void *actions_host, const ds_params *
     DS_CUDA(cudaMemcpyAsync(host_block, dev_block, bytes, cudaMemcpyDeviceToHost, st));
     DS_CUDA(cudaStreamSynchronize(st));
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_step_host_block: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_step_host_block: unknown host exception");
 }
 
 int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, const ds_host_rollout *hr,
                     void *cuda_stream)
-{
+try {
     if (!h || !hr || !io) return fail(DS_ERR_ARG, "ds_rollout_host: NULL argument");
     if (int rc = check_params(p)) return rc;
     if (hr->T < 0) return fail(DS_ERR_ARG, "ds_rollout_host: T < 0");
@@ -1051,14 +1120,24 @@ int ds_rollout_host(ds_handle *h, const ds_params *p, const ds_buffers *io, cons
             }
         };
         std::vector<std::thread> pool;
-        for (int w = 1; w < nth; ++w) pool.emplace_back(fill, total * w / nth, total * (w + 1) / nth);
+        pool.reserve(nth);
+        int spawned = 1;                                              // part 0 is this thread's
+        try {
+            for (; spawned < nth; ++spawned) pool.emplace_back(fill, total * spawned / nth, total * (spawned + 1) / nth);
+        } catch (...) {                                               // no more threads: this one does the rest
+        }
         fill(0, total / nth);
+        if (spawned < nth) fill(total * spawned / nth, total);
         for (auto &t : pool) t.join();
     }
     DS_CUDA(cudaStreamSynchronize(st));
     DS_CUDA(cudaStreamSynchronize(h->s_d2h));
     DS_CUDA(cudaStreamSynchronize(h->s_h2d));
     return DS_OK;
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_rollout_host: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_rollout_host: unknown host exception");
 }
 
 }  // extern "C"
