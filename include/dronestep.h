@@ -144,6 +144,10 @@ int ds_step(ds_handle *h, const void *actions_dev, const ds_params *p,
  *   DS_CTRL_GRADIENT      gradient_control(state, env, u_max)     drone_env.py:612-653 */
 #define DS_CTRL_PROPORTIONAL 1
 #define DS_CTRL_GRADIENT 2
+/* Only the controller: actions_out_dev[E][n][2] = controller(current io->pos); nothing is stepped
+ * (what the reference's module-level gradient_control / proportional_control return). */
+int ds_control(ds_handle *h, int controller, double u_max, const ds_buffers *io,
+               void *actions_out_dev, void *cuda_stream);
 int ds_step_control(ds_handle *h, int controller, double u_max, const ds_params *p,
                     const ds_buffers *io, void *cuda_stream);
 /* T closed-loop steps in one launch (the episode loop with `actions = gradient_control(state, env)`,

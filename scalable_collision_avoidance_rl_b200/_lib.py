@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "ds_default_params", "ds_step", "ds_observe", "ds_rollout", "ds_reduce_aggregates",
     "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_step_host_block", "ds_rollout_host", "ds_returns",
     "ds_step_control", "ds_rollout_control", "ds_reset_random",
-    "ds_policy_create", "ds_policy_destroy", "ds_policy_forward", "ds_rollout_policy",
+    "ds_policy_create", "ds_policy_destroy", "ds_policy_forward", "ds_rollout_policy", "ds_control",
 )
 
 

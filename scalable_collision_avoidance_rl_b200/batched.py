@@ -220,6 +220,18 @@ class BatchedDrones:
         return ((self.pos, self.vel), self.z_states, self.rewards, self.n_collisions, self.finished,
                 self.true_rewards)
 
+    def control(self, controller="gradient", u_max=1.0, out=None):
+        """Actions of one of the reference's baseline controllers on the current state, computed on
+        the device (ds_control; drone_env.py:612-679) -> [E,n,2]; nothing is stepped."""
+        mode = {"proportional": _lib.DS_CTRL_PROPORTIONAL, "gradient": _lib.DS_CTRL_GRADIENT}.get(controller)
+        if mode is None:
+            raise ValueError("controller must be 'proportional' or 'gradient'")
+        if out is None:
+            out = torch.empty((self.n_envs, self.n_agents, 2), dtype=self.dtype, device=self.device)
+        _lib.check(self.lib.ds_control(self._h, mode, ctypes.c_double(u_max), ctypes.byref(self._io), _ptr(out),
+                                       self._stream()), "ds_control")
+        return out
+
     def step_control(self, controller="gradient", u_max=1.0):
         """One closed-loop step: actions computed on the device by one of the reference's baseline
         controllers (drone_env.py:612-679: "proportional" | "gradient"), then drones.step()

@@ -223,7 +223,7 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
         return fail(DS_ERR_ARG, "ds_buffers: finished/t must be non-NULL for a step");
     a->E = h->E; a->n = h->n; a->k = h->k; a->simplify = h->simplify; a->G = h->step_G;
     a->do_integrate = integrate ? 1 : 0;
-    a->ctrl = 0; a->u_max = 1.0;
+    a->ctrl = 0; a->u_max = 1.0; a->ctrl_out = nullptr;
     a->log_mode = p->log_mode;
     a->max_steps = p->max_time_steps;
     a->c = ds::Consts{h->d_xF, h->d_ds, h->d_delta, h->d_radius, h->d_logds, h->d_thr2, h->d_clipcnt, h->d_logtab};
@@ -451,6 +451,22 @@ try {
     return fail(DS_ERR_INTERNAL, std::string("ds_step_control: host exception: ") + ex.what());
 } catch (...) {
     return fail(DS_ERR_INTERNAL, "ds_step_control: unknown host exception");
+}
+
+int ds_control(ds_handle *h, int controller, double u_max, const ds_buffers *io, void *actions_out_dev,
+               void *cuda_stream)
+{
+    ds_params p;
+    ds_default_params(&p);
+    ds::StepArgs a;
+    if (int rc = fill_step_args(h, &p, io, nullptr, false, &a)) return rc;
+    if (controller != DS_CTRL_PROPORTIONAL && controller != DS_CTRL_GRADIENT)
+        return fail(DS_ERR_ARG, "ds_control: controller must be DS_CTRL_PROPORTIONAL or DS_CTRL_GRADIENT");
+    if (!(u_max >= 0)) return fail(DS_ERR_ARG, "ds_control: u_max must be >= 0");
+    if (!actions_out_dev) return fail(DS_ERR_ARG, "ds_control: actions_out_dev is NULL");
+    a.ctrl = controller; a.u_max = u_max; a.ctrl_out = actions_out_dev;
+    DeviceGuard guard(h->device);
+    return launch_step(h, a, (cudaStream_t)cuda_stream);
 }
 
 static int launch_rollout_control(ds_handle *h, const ds::RolloutArgs &ra, const Geom &gm, cudaStream_t st)

@@ -271,6 +271,7 @@ struct StepArgs {
     int E, n, k, simplify, G, do_integrate, log_mode, max_steps;
     int ctrl;                // 0: actions given; 1 / 2: the reference's proportional / gradient controller
     double u_max;            // gradient controller's clip (drone_env.py:612)
+    void *ctrl_out;          // non-null: only compute the controller's actions -> Real [E][n][2], no step
     Consts c;
     double dt, q, b, goal_tol, sentinel, zero_eps, ghost;
     const void *act;         // Real [E][n][2]
@@ -835,6 +836,10 @@ step_kernel(const StepArgs a)
             const V2 p = sm.pos[lt];
             control_action<Real>(a.ctrl, n, i, p.x, p.y, c.xF, c.yF, c.ds, c.radius, sm.pos + le * n, sm.radius, 1,
                                  (Real)a.u_max, u_ctrl.x, u_ctrl.y);
+        }
+        if (a.ctrl_out) {                                  // ds_control: the actions are the result
+            if (active) reinterpret_cast<V2 *>(a.ctrl_out)[g] = u_ctrl;
+            return;
         }
         __syncthreads();                                   // everybody has read the old positions
     }

@@ -247,41 +247,27 @@ class drones:
 
 
 # ---------------------------------------------------------------------- controllers (drone_env.py:612-679)
+def _device_control(controller, state, env, u_max):
+    """Both baseline controllers run on the device (ds_control) for the one environment of `env`."""
+    state = np.asarray(state, np.float64)
+    if not np.array_equal(state[:, 4], env.drone_radius):
+        raise ValueError("the controllers take the agent radii from state[:, 4] (drone_env.py:632,643); "
+                         "this build holds them as the constants env.drone_radius and the two differ")
+    eng = env._engine(env.end_points, env.d_safety, env.deltas)
+    env._synced = None                                   # the device state is overwritten below
+    eng.set_state(np.asarray(state, np.float64)[None], internal_t=env.internal_t)
+    act = eng.control(controller, float(u_max))[0].cpu().numpy()
+    return [act[i].copy() for i in range(env.n_agents)]
+
+
 def gradient_control(state, env, u_max=1):
     """Descent direction of the log-barrier cost with global knowledge (drone_env.py:612-653)."""
-    b, q = 0.1, 1
-    n = env.n_agents
-    x = np.asarray(state)[:, 0:dim]
-    rad = np.asarray(state)[:, 4]
-    xF = env.end_points.reshape(n, dim)
-    actions = []
-    for i in range(n):
-        pull = 2 * (x[i] - xF[i])
-        push = np.zeros(dim)
-        for j in range(n):
-            if j == i:
-                continue
-            sep = np.linalg.norm(x[i] - x[j])
-            dij = sep - rad[i] - rad[j]
-            if dij <= env.d_safety[i]:
-                push += (x[i] - x[j]) / (dij * sep)
-        actions.append(np.clip(-(q * pull - b * push), -u_max, u_max))
-    return actions
+    return _device_control("gradient", state, env, u_max)
 
 
 def proportional_control(state, env):
     """Unit-gain P controller with the control norm capped at 1 m/s (drone_env.py:655-679)."""
-    u_max, gain = 1, 1
-    n = env.n_agents
-    xF = env.end_points.reshape(n, dim)
-    actions = []
-    for i in range(n):
-        u = gain * (xF[i] - np.asarray(state)[i, 0:dim])
-        norm = np.linalg.norm(u)
-        if norm > u_max:
-            u = u / norm * u_max
-        actions.append(u)
-    return actions
+    return _device_control("proportional", state, env, 1.0)
 
 
 # ---------------------------------------------------------------------- plotting helpers (drone_env.py:682-741)

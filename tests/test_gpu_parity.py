@@ -574,6 +574,30 @@ def test_closed_loop_rollout_equals_stepping(ctrl, n, E, grid):
     assert_close(out["agg"].cpu().numpy(), sums, 1e-9, "episode sums")
 
 
+@pytest.mark.parametrize("name,key,fn", [("control_gradient_n5", "action", "gradient"),
+                                         ("control_proportional_n8", "action", "proportional"),
+                                         ("control_dense_n7", "gradient", "gradient"),
+                                         ("control_dense_n7", "proportional", "proportional")])
+def test_dropin_controller_functions_vs_reference_golden(name, key, fn):
+    """drone_env.gradient_control / proportional_control of the drop-in module (ds_control on the
+    device) return, bit for bit, what the reference's functions returned on the recorded states
+    (NaN patterns at exact contact / on the goal included)."""
+    import os
+    import drone_env
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    n = int(g["n"])
+    env = drone_env.drones(n, 0, [float(x) for x in g["grid"]], "O", 2, np.ones(n) * float(g["delta"]), True)
+    assert np.array_equal(env.end_points, g["end_points"]) and np.array_equal(env.d_safety, g["d_safety"])
+    frames = range(0, g["state_in"].shape[0], max(1, g["state_in"].shape[0] // 12))
+    for f in frames:
+        if fn == "gradient":
+            act = drone_env.gradient_control(g["state_in"][f], env, u_max=float(g["u_max"]))
+        else:
+            act = drone_env.proportional_control(g["state_in"][f], env)
+        assert len(act) == n and act[0].shape == (2,)
+        assert np.array_equal(np.array(act), g[key][f], equal_nan=True), f"frame {f}"
+
+
 def test_controllers_vs_oracle_dense_batch():
     """Both controllers on dense random batches (many pairs inside d_safety) against the oracle,
     through the closed-loop step: the action taken is left in vel."""
