@@ -833,7 +833,10 @@ static int check_policy(const char *who, ds_handle *h, ds_policy *pol)
 
 static int launch_policy(ds_handle *h, ds_policy *pol, const ds::PolicyArgs &a, cudaStream_t st)
 {
-    const dim3 grid((h->E + 127) / 128, h->n);
+    if (h->E <= 0) return DS_OK;
+    // persistent: one CTA per SM walks a contiguous range of (agent, 128-environment) tiles
+    const long long tiles = (long long)((h->E + 127) / 128) * h->n;
+    const dim3 grid((unsigned)std::min<long long>(tiles, h->sm_count));
     const size_t smem = sizeof(ds::PolicySmem) + 128;
 #define DS_POLICY_LAUNCH(REAL, IN)                                                                      \
     do {                                                                                                \
@@ -860,6 +863,7 @@ static ds::PolicyArgs policy_args(ds_handle *h, ds_policy *pol)
     std::memset(&a, 0, sizeof a);
     a.E = h->E; a.n = h->n; a.in_dim = pol->in_dim; a.n_actions = pol->A; a.real_bytes = h->real_bytes;
     a.head = pol->head; a.W2p = pol->W2p; a.W3t = pol->W3t; a.atable = pol->atable;
+    a.tiles_per_agent = (h->E + 127) / 128;
     return a;
 }
 

@@ -8,7 +8,8 @@
 //   it once per agent per step on the host (SAC_agents.py:60-82,170-180).
 // Batched over E environments the 300 x 300 layer is a grouped GEMM -- n groups (one network per
 // agent), M = E rows each -- and belongs on tcgen05:
-//   * one CTA = one agent x one tile of 128 environments (M = 128 = the TMEM lanes); the W2 chunks
+//   * a tile = one agent x 128 environments (M = 128 = the TMEM lanes); persistent CTAs (one per SM)
+//     walk contiguous ranges of tiles; the W2 chunks
 //     arrive by TMA bulk copies (cp.async.bulk, double buffered, counted on an mbarrier);
 //     warps 0-3 own the 128 rows, one thread of warp 4 issues copies and MMAs (no CTA barrier
 //     in the main loop: mbarrier handshakes both ways);
@@ -45,6 +46,7 @@ constexpr int kPolHeadFloats = kPolHeadB3 + kPolMaxA;          // 5760 floats = 
 struct PolicyArgs {
     int E, n, in_dim, n_actions, real_bytes;
     unsigned seed_lo, seed_hi, stream;
+    int tiles_per_agent;      // ceil(E / 128); tile t = (agent t / tiles_per_agent, environments 128 (t % tiles_per_agent) ..)
     const unsigned long long *seed_dev;   // when non-null the seed is read from device memory (graph replays)
     const void *z;            // Real [E][n][in_dim]
     const float *head;        // [n][kPolHeadFloats]
@@ -86,8 +88,9 @@ struct PolicySmem {
     float W1t[kPolMaxIn][kPolKP];                            // the head block, in ds_policy_create's order (22.5 KB)
     float b1[kPolKP], b2[kPolNP], b3[kPolMaxA];
     float W3t[kPolNP][kPolMaxA];                             // 19 KB
-    unsigned long long full[2], mma_done[2], a_ready[2], params;   // mbarriers: W2 chunk landed / MMAs of a half-chunk done /
-                                                             // A half written by the 128 rows / head + W3t landed
+    unsigned long long full[2], mma_done[2], a_ready[2], params, rows_done;   // mbarriers: W2 chunk landed / MMAs of a
+                                                             // half-chunk done / A half written by the 128 rows / head + W3t
+                                                             // landed / the rows have left a tile (parameters may change)
     uint32_t tmem_base;
 };
 static_assert(offsetof(PolicySmem, b1) - offsetof(PolicySmem, W1t) == kPolHeadB1 * sizeof(float) &&
@@ -163,6 +166,11 @@ __device__ __forceinline__ void pol_layer3_block(float2 (&lg)[kPolMaxA / 2], con
 // thread that issues the bulk copies and the MMAs.  The main loop has no CTA barrier: rows -> issuer
 // through a_ready (128 arrivals), issuer -> rows through tcgen05.commit on mma_done.
 constexpr int kPolThreads = 160;
+// PERSISTENT: the grid has one CTA per SM (or per tile, if fewer); a CTA walks a contiguous range of
+// tiles, so that consecutive tiles mostly belong to the same agent: the parameter block stays in
+// shared memory, the W2 ring simply continues (chunks 0 and 1 of the next tile arrive during the
+// epilogue of the current one), TMEM and the mbarriers are set up once.  Step and chunk counters run
+// across tiles; every mbarrier parity is derived from them.
 template <typename Real, int IN>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(const PolicyArgs a)
 {
@@ -170,15 +178,29 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(const PolicyArgs
     extern __shared__ __align__(128) unsigned char pol_smem_raw[];
     PolicySmem &sm = *reinterpret_cast<PolicySmem *>(pol_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int agent = blockIdx.y;
     const bool row_thread = tid < 128, issuer = tid == 128;
-    const int e = blockIdx.x * 128 + tid;                    // a row thread's environment = TMEM lane tid
-    const bool live = row_thread && e < a.E;
-    const int in_dim = a.in_dim, A = a.n_actions;
+    const int in_dim = a.in_dim, A = a.n_actions, TPA = a.tiles_per_agent;
+    const long long total = (long long)a.n * TPA;
+    const int t_begin = (int)(total * blockIdx.x / gridDim.x), t_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    constexpr int NST = 2 * (kPolKP / kPolChunk);            // 20 half-chunks of 16 hidden units (= 16 of K) per tile
+    constexpr int NCH = kPolKP / kPolChunk;                  // 10 W2 chunks per tile
+    constexpr size_t kChunkFloats = kPolChunkBytes / sizeof(float);
+    auto w2_of = [&](int agent) { return a.W2p + (size_t)agent * NCH * kChunkFloats; };
+    auto load_params = [&](int agent) {
+        pol_expect(&sm.params, kPolHeadBytes + kPolW3tBytes);
+        pol_bulk_copy(&sm.W1t[0][0], a.head + (size_t)agent * kPolHeadFloats, kPolHeadBytes, &sm.params);
+        pol_bulk_copy(&sm.W3t[0][0], a.W3t + (size_t)agent * kPolNP * kPolMaxA, kPolW3tBytes, &sm.params);
+    };
+    // observation of a row thread's (environment, agent) of tile t: float32(z) as the reference casts it (utils.py:305)
+    auto load_z = [&](float (&zz)[kPolMaxIn], int t) {
+        const int agent = t / TPA, e = (t - agent * TPA) * 128 + tid;
+        const bool ok = row_thread && t < t_end && e < a.E;
+#pragma unroll
+        for (int d = 0; d < kPolMaxIn; ++d)
+            zz[d] = (ok && d < in_dim) ? (float)reinterpret_cast<const Real *>(a.z)[((size_t)e * a.n + agent) * in_dim + d] : 0.f;
+    };
 
-    // ---- mbarriers, TMEM, and the first copies: parameter block + W3t, W2 chunks 0 and 1
-    const float *W2p = a.W2p + (size_t)agent * (kPolKP / kPolChunk) * (kPolChunkBytes / sizeof(float));
-    constexpr int NST = 2 * (kPolKP / kPolChunk);            // 20 half-chunks of 16 hidden units (= 16 of K)
+    // ---- once per CTA: mbarriers, TMEM, parameter block and W2 chunks 0 and 1 of the first tile
     if (issuer) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.full[1])));
@@ -187,68 +209,90 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(const PolicyArgs
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pol_smem_u32(&sm.a_ready[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pol_smem_u32(&sm.a_ready[1])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pol_smem_u32(&sm.params)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" ::"r"(pol_smem_u32(&sm.rows_done)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        pol_expect(&sm.params, kPolHeadBytes + kPolW3tBytes);
-        pol_bulk_copy(&sm.W1t[0][0], a.head + (size_t)agent * kPolHeadFloats, kPolHeadBytes, &sm.params);
-        pol_bulk_copy(&sm.W3t[0][0], a.W3t + (size_t)agent * kPolNP * kPolMaxA, kPolW3tBytes, &sm.params);
-        pol_bulk_load(&sm.B[0][0][0][0][0], W2p, kPolChunkBytes, &sm.full[0]);
-        pol_bulk_load(&sm.B[1][0][0][0][0], W2p + kPolChunkBytes / sizeof(float), kPolChunkBytes, &sm.full[1]);
+        const int agent0 = t_begin / TPA;
+        load_params(agent0);
+        pol_bulk_load(&sm.B[0][0][0][0][0], w2_of(agent0), kPolChunkBytes, &sm.full[0]);
+        pol_bulk_load(&sm.B[1][0][0][0][0], w2_of(agent0) + kChunkFloats, kPolChunkBytes, &sm.full[1]);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(pol_smem_u32(&sm.tmem_base)),
                      "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // observation of this thread's (environment, agent): float32(z) as the reference casts it (utils.py:305)
-    float zin[kPolMaxIn];
-#pragma unroll
-    for (int d = 0; d < kPolMaxIn; ++d)
-        zin[d] = (live && d < in_dim) ? (float)reinterpret_cast<const Real *>(a.z)[((size_t)e * a.n + agent) * in_dim + d] : 0.f;
+    float zin[kPolMaxIn], znext[kPolMaxIn];
+    load_z(znext, t_begin);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sm.tmem_base;
 
     if (issuer) {
-        // ---- layer 2: MMAs of step s from A half (s & 1) as soon as the rows have written it.  W2 arrives
-        // in chunks of 32 (two steps); the chunk of step s + 2 is copied into the buffer that the MMAs of
-        // step s - 1 were the last to read.
-        for (int s_ = 0; s_ < NST; ++s_) {
-            const int ab = s_ & 1, kc = s_ >> 1, bsel = kc & 1;
-            if (ab == 0) pol_wait(pol_smem_u32(&sm.full[bsel]), (uint32_t)(kc >> 1) & 1u);   // W2 chunk kc has landed
-            pol_wait(pol_smem_u32(&sm.a_ready[ab]), (uint32_t)(s_ >> 1) & 1u);              // A half written, fenced
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {                                     // one MMA = K of 8 = 2 k-groups
-                const uint64_t a_hi = pol_desc(&sm.A_hi[ab][2 * ks][0][0], 128 * 16, 128);
-                const uint64_t a_lo = pol_desc(&sm.A_lo[ab][2 * ks][0][0], 128 * 16, 128);
-                const int kgb = 4 * ab + 2 * ks;                                 // k-group inside the W2 chunk
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {                           // N = 160 + 144
-                    const int row0 = half ? 160 : 0, N = half ? 144 : 160;
-                    const uint64_t b_hi = pol_desc(&sm.B[bsel][0][kgb][row0][0], kPolNP * 16, 128);
-                    const uint64_t b_lo = pol_desc(&sm.B[bsel][1][kgb][row0][0], kPolNP * 16, 128);
-                    const uint32_t idesc = pol_idesc(N), d = tmem + (uint32_t)row0;
-                    pol_mma(d, a_hi, b_hi, idesc, (s_ | ks) != 0);
-                    pol_mma(d, a_hi, b_lo, idesc, 1);
-                    pol_mma(d, a_lo, b_hi, idesc, 1);
-                }
+        // ---- layer 2: MMAs of step s from A half (s & 1) as soon as the rows have written it.  W2 arrives in
+        // chunks of 32 (two steps); the next chunk of the ring is copied into the buffer that the MMAs of the
+        // previous step were the last to read.
+        unsigned gs = 0;                                                     // steps issued so far (all tiles)
+        for (int t = t_begin; t < t_end; ++t) {
+            const int agent = t / TPA;
+            const float *W2p = w2_of(agent);
+            if (t > t_begin && agent != (t - 1) / TPA) {
+                // new agent: its parameter block may land once every row has left the previous tile
+                pol_wait(pol_smem_u32(&sm.rows_done), (uint32_t)(t - t_begin - 1) & 1u);
+                load_params(agent);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                pol_smem_u32(&sm.mma_done[ab])));
-            if (ab == 0 && s_ >= 2 && kc + 1 < NST / 2) {
-                pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((s_ - 1) >> 1) & 1u);
-                pol_bulk_load(&sm.B[bsel ^ 1][0][0][0][0], W2p + (size_t)(kc + 1) * (kPolChunkBytes / sizeof(float)),
-                              kPolChunkBytes, &sm.full[bsel ^ 1]);
+            for (int s_ = 0; s_ < NST; ++s_, ++gs) {
+                const int ab = s_ & 1, kc = s_ >> 1, bsel = kc & 1;
+                const unsigned g = (unsigned)(t - t_begin) * NCH + (unsigned)kc;    // chunk number in the ring
+                if (ab == 0) pol_wait(pol_smem_u32(&sm.full[bsel]), (g >> 1) & 1u);  // W2 chunk has landed
+                pol_wait(pol_smem_u32(&sm.a_ready[ab]), (gs >> 1) & 1u);             // A half written, fenced
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {                                     // one MMA = K of 8 = 2 k-groups
+                    const uint64_t a_hi = pol_desc(&sm.A_hi[ab][2 * ks][0][0], 128 * 16, 128);
+                    const uint64_t a_lo = pol_desc(&sm.A_lo[ab][2 * ks][0][0], 128 * 16, 128);
+                    const int kgb = 4 * ab + 2 * ks;                                 // k-group inside the W2 chunk
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {                           // N = 160 + 144
+                        const int row0 = half ? 160 : 0, N = half ? 144 : 160;
+                        const uint64_t b_hi = pol_desc(&sm.B[bsel][0][kgb][row0][0], kPolNP * 16, 128);
+                        const uint64_t b_lo = pol_desc(&sm.B[bsel][1][kgb][row0][0], kPolNP * 16, 128);
+                        const uint32_t idesc = pol_idesc(N), d = tmem + (uint32_t)row0;
+                        pol_mma(d, a_hi, b_hi, idesc, (s_ | ks) != 0);
+                        pol_mma(d, a_hi, b_lo, idesc, 1);
+                        pol_mma(d, a_lo, b_hi, idesc, 1);
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                    pol_smem_u32(&sm.mma_done[ab])));
+                if (ab == 0 && gs >= 2) {
+                    const float *next = (kc + 1 < NCH) ? W2p + (size_t)(kc + 1) * kChunkFloats
+                                                       : (t + 1 < t_end ? w2_of((t + 1) / TPA) : nullptr);
+                    if (next) {
+                        pol_wait(pol_smem_u32(&sm.mma_done[1]), ((gs - 1) >> 1) & 1u);
+                        pol_bulk_load(&sm.B[bsel ^ 1][0][0][0][0], next, kPolChunkBytes, &sm.full[bsel ^ 1]);
+                    }
+                }
             }
         }
     } else if (row_thread) {
-        pol_wait(pol_smem_u32(&sm.params), 0u);
+        unsigned gs = 0, nparam = 0;
+        int prev_agent = -1;
+        for (int t = t_begin; t < t_end; ++t) {
+        const int agent = t / TPA;
+        const int e = (t - agent * TPA) * 128 + tid;             // this thread's environment = TMEM lane tid
+        const bool live = e < a.E;
+        if (agent != prev_agent) {                               // the parameter block of this agent has landed
+            pol_wait(pol_smem_u32(&sm.params), nparam & 1u);
+            ++nparam; prev_agent = agent;
+        }
+#pragma unroll
+        for (int d = 0; d < kPolMaxIn; ++d) zin[d] = znext[d];
         // ---- layer 1 for this thread's environment, 16 units per step (utils.py:289-290), split hi / lo
-        for (int s_ = 0; s_ < NST; ++s_) {
+        for (int s_ = 0; s_ < NST; ++s_, ++gs) {
             const int ab = s_ & 1;
-            // A half ab was last read by the MMAs of step s - 2
-            if (s_ >= 2) pol_wait(pol_smem_u32(&sm.mma_done[ab]), (uint32_t)((s_ >> 1) - 1) & 1u);
+            // A half ab was last read by the MMAs of step gs - 2
+            if (gs >= 2) pol_wait(pol_smem_u32(&sm.mma_done[ab]), ((gs >> 1) - 1) & 1u);
 #pragma unroll
             for (int kg = 0; kg < 4; ++kg) {
                 const int j0 = s_ * 16 + kg * 4;                                 // units j0 .. j0 + 3 (padding: 0 weights)
@@ -274,10 +318,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(const PolicyArgs
                 *reinterpret_cast<float4 *>(&sm.A_lo[ab][kg][tid][0]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic stores -> async proxy
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // (the previous tile's TMEM reads)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pol_smem_u32(&sm.a_ready[ab])) : "memory");
         }
+        load_z(znext, t + 1);                                    // the next tile's observation, in flight during the epilogue
         // D may be read once the MMAs of the last step (and with them all earlier ones) are done
-        pol_wait(pol_smem_u32(&sm.mma_done[1]), (uint32_t)((NST - 1) >> 1) & 1u);
+        pol_wait(pol_smem_u32(&sm.mma_done[1]), ((gs - 1) >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: row e of D -> +b2, ReLU -> layer 3 on the CUDA cores; the tcgen05.ld of the next
@@ -330,6 +376,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(const PolicyArgs
         reinterpret_cast<V2 *>(a.act)[ga] = reinterpret_cast<const V2 *>(a.atable)[pick];   // action_list[arg] (:309)
         if (a.aidx) a.aidx[ga] = (uint8_t)pick;
     }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pol_smem_u32(&sm.rows_done)) : "memory");
+        }   // tiles
     }   // row threads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

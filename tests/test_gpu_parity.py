@@ -708,7 +708,10 @@ def test_policy_forward_vs_reference_golden():
 
 
 @pytest.mark.parametrize("n,E,k,simplify,A", [(10, 1000, 2, True, 16), (5, 129, 2, False, 8), (32, 300, 1, True, 5),
-                                              (5, 1, 4, True, 16), (9, 7, 7, True, 3), (4, 128, 0, True, 1)])
+                                              (5, 1, 4, True, 16), (9, 7, 7, True, 3), (4, 128, 0, True, 1),
+                                              # more tiles than SMs: persistent CTAs walk several tiles and
+                                              # cross from one agent's network to the next
+                                              (10, 2567, 2, True, 16), (5, 15360, 2, True, 8)])
 def test_policy_forward_vs_fp32_restatement(n, E, k, simplify, A):
     """Random torch-style weights (layers 2 and 3 scaled x3 to spread the logits), one network per
     agent, E not a multiple of the 128-row tile: probabilities against the fp32 NumPy restatement
