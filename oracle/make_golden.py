@@ -216,10 +216,19 @@ def main():
                          note="heterogeneous deltas: N_delta uses deltas[j]")
     dense_teacher_forced("dense_n33_g32", 33, [32, 32], np.ones(33) * 2.5, 6, 6.0, seed=10)
     edge_cases("edge_cases_n4")
-    for seed in (0, 1):
-        policy_episode(f"policy_n5_seed{seed}", seed)
+    policy_episodes()
     ctor_table()
 
 
+def policy_episodes(seeds=range(10)):
+    """BASELINE config 1 as SURVEY section 8(d) states it: seeds 0..9."""
+    os.makedirs(OUT, exist_ok=True)
+    for seed in seeds:
+        policy_episode(f"policy_n5_seed{seed}", seed)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--policy-only":      # add seeds without touching the other fixtures
+        policy_episodes([int(x) for x in sys.argv[2:]] or range(10))
+    else:
+        main()
