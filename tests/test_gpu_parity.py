@@ -52,8 +52,8 @@ def test_step_vs_reference_golden(name, log_mode):
     compare_obs(z.cpu().numpy(), env.Ni.cpu().numpy(), g["z"], g["Ni"], g["tie"], FP64_TOL, name)
 
 
-@pytest.mark.parametrize("name", ["policy_n5_seed0", "policy_n5_seed1", "free_n10_g5_d1.0",
-                                  "free_n8_g5_d1.0_k3_cw0.5", "free_n5_g5_dNone_full"])
+@pytest.mark.parametrize("name", [f"policy_n5_seed{s}" for s in range(10)] +
+                         ["free_n10_g5_d1.0", "free_n8_g5_d1.0_k3_cw0.5", "free_n5_g5_dNone_full"])
 def test_dropin_class_lockstep(name):
     """The reference-facing class `drone_env.drones`, free-running a whole recorded episode
     (BASELINE config 1 for the policy_* fixtures) with only the action stream shared."""
