@@ -39,6 +39,41 @@ CASES = [  # n, grid, k, simplify, deltas ("u" = uniform 1.0, "h" = heterogeneou
 ]
 
 
+from test_row_logic_host import rowlib, _frame  # noqa: E402,F401  (fixture + host build of the kernels' row logic)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c[0]}_k{c[2]}_{'s' if c[3] else 'f'}_{c[4]}_{c[5]}")
+@pytest.mark.parametrize("path", [0, 1, 2], ids=["row", "worklist", "inline32"])
+def test_kernel_row_logic_against_the_live_reference(rowlib, case, path):
+    """The row logic of the CUDA kernels (dronestep_kernels.cuh compiled for the host, as in
+    test_row_logic_host.py) evaluated on states the live reference has just produced."""
+    if path == 2 and case[0] > 32:
+        pytest.skip("inline mode exists for n <= 32 only")
+    from oracle.ref_harness import import_reference
+    ref = import_reference("drone_env")
+    n, grid, k, simplify, dmode, box, cw = case
+    rng = np.random.default_rng(77 + n)
+    deltas = None if dmode is None else (np.ones(n) if dmode == "u" else rng.uniform(0.2, 2.0, n))
+    random.seed(5); np.random.seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = ref.drones(n_agents=n, n_obstacles=0, grid=list(grid), end_formation="O", k_closest=k,
+                         deltas=None if deltas is None else deltas.copy(), simplify_zstate=simplify)
+    env.collision_weight = cw
+    if box is not None:
+        env.state[:, 0:2] = rng.uniform(0, box, (n, 2))
+    dl = np.asarray(env.deltas, np.float64).reshape(-1)
+    for step in range(12):
+        act = rng.uniform(-1, 1, (n, 2))
+        state, z, r, ncoll, fin, tr = env.step([a_.copy() for a_ in act])
+        got_r, got_tr, got_z, got_Ni, nc, _ = _frame(rowlib, path, 8, n, k, simplify, 0, state[:, 0:2].copy(),
+                                                     state[:, 2:4].copy(), env.end_points.reshape(n, 2),
+                                                     env.d_safety, dl, env.drone_radius, cw)
+        assert_close(got_r, np.array(r), FP64_TOL, f"r step {step}")
+        assert_close(got_tr, np.array(tr), FP64_TOL, f"true_r step {step}")
+        assert nc == int(ncoll), step
+        _compare_obs_live(env, got_z, got_Ni, np.array(z), _pad(env.Ni, k), f"obs step {step}")
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"n{c[0]}_k{c[2]}_{'s' if c[3] else 'f'}_{c[4]}_{c[5]}")
 @pytest.mark.parametrize("seed", [11, 12])
 def test_c_oracle_against_the_live_reference(case, seed):
