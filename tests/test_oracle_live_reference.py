@@ -135,3 +135,37 @@ def _compare_obs_live(env, z, Ni, z_ref, Ni_ref, what):
             if cols == 5:
                 assert np.array_equal(z[i, kth, 2:5], env.state[j, 2:5]), f"{what}: row {i} slot {kth} velocity / radius"
         assert len({int(j) for j in Ni[i] if j >= 0}) == (Ni[i] >= 0).sum(), f"{what}: duplicate agent row {i}"
+
+
+@pytest.mark.parametrize("n,grid,box,u_max", [(5, [5, 5], 2.0, 1.0), (11, [6, 6], 1.5, 0.7), (33, [32, 32], 6.0, 1.0)])
+def test_controllers_against_the_live_reference(rowlib, n, grid, box, u_max):
+    """control_action of the kernels (host build) and the C oracle against the reference's own
+    gradient_control / proportional_control (drone_env.py:612-679) on dense random states: bit-exact,
+    NaN patterns included."""
+    import ctypes
+    from oracle.ref_harness import import_reference
+    ref = import_reference("drone_env")
+    rng = np.random.default_rng(n)
+    random.seed(1); np.random.seed(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = ref.drones(n_agents=n, n_obstacles=0, grid=list(grid), end_formation="O", k_closest=2,
+                         deltas=np.ones(n), simplify_zstate=True)
+    xF = np.ascontiguousarray(env.end_points.reshape(-1)); dsf = np.ascontiguousarray(env.d_safety)
+    rad = np.ascontiguousarray(env.drone_radius)
+    for f in range(20):
+        env.state[:, 0:2] = rng.uniform(0, box, (n, 2))
+        if f == 3:
+            env.state[1, 0:2] = env.state[0, 0:2] + [rad[0] + rad[1], 0.0]      # exact contact: division by zero
+        if f == 4:
+            env.state[2, 0:2] = env.end_points.reshape(n, 2)[2]                  # on the goal
+        with np.errstate(all="ignore"):
+            want = {2: np.array(ref.gradient_control(env.state, env, u_max=u_max)).reshape(n, 2),
+                    1: np.array(ref.proportional_control(env.state, env)).reshape(n, 2)}
+        pos = np.ascontiguousarray(env.state[:, 0:2])
+        for mode, um in ((2, u_max), (1, 1.0)):
+            act = np.zeros((n, 2))
+            rowlib.rowcheck_control(mode, n, *[x.ctypes.data_as(ctypes.c_void_p) for x in (pos, xF, dsf, rad)],
+                                    ctypes.c_double(um), act.ctypes.data_as(ctypes.c_void_p))
+            assert np.array_equal(act, want[mode], equal_nan=True), (f, mode)
+            got = c_oracle.control(mode, pos[None], env.end_points, env.d_safety, None, um)[0]
+            assert np.array_equal(got, want[mode], equal_nan=True), (f, mode, "oracle")
