@@ -16,8 +16,11 @@ import succeed on this image:
      NumPy 2),
   3. stub ``turtle`` and ``autograd`` for ``utils.py:2,4-5`` (policy side).
 
-``/root/reference`` does not exist on the GPU box: nothing under ``tests/ -m
-gpu``, ``__graft_entry__.smoke()`` or ``bench.py`` may import this module.
+``/root/reference`` does not exist on the GPU box.  What travels there is the git-ignored
+staging copy ``oracle/_ref/`` written by ``oracle/make_ref.py`` (unmodified files); this module
+falls back to it, so that ``bench.py``'s CPU-baseline legs and the one ``-m gpu`` test that drives
+the reference's own agents can run the real reference beside the GPU.  The product package never
+imports this module.
 """
 from __future__ import annotations
 
@@ -27,7 +30,11 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = os.environ.get("DRONESTEP_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "drone_env.py")) and \
+        os.path.isfile(os.path.join(_STAGED, "drone_env.py")):
+    REFERENCE_ROOT = _STAGED          # GPU box: the staged, unmodified copy (oracle/make_ref.py)
 
 
 def reference_available() -> bool:
