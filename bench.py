@@ -565,6 +565,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--log-mode", type=int, default=0)
     ap.add_argument("--episode-steps", type=int, default=0, help="env-steps per episode / rollout launch (default 200)")
+    ap.add_argument("--envs", type=int, default=0, help="override the workload's environment count (tuning runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config4 / config5 legs")
@@ -574,7 +575,9 @@ def main():
                     help="--impl reference: upper bound on the CPU time of one step's sample")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.envs:
+        wl["E"] = args.envs
     if args.impl == "reference":
         run_reference(args, wl)
     else:

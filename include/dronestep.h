@@ -56,6 +56,7 @@ extern "C" {
 /* log(d_safety/d_ij) evaluation (reference drone_env.py:321,331) */
 #define DS_LOG_DIV 0    /* log(d_safety / d): same operation order as the reference */
 #define DS_LOG_DIFF 1   /* log|d_safety| - log|d|: no division, <= 4e-16 absolute difference */
+#define DS_LOG_RCP 2    /* -log(d * (1 / d_safety)), reciprocal rounded once: no division, <= 3.4e-16 absolute difference */
 
 typedef struct ds_handle ds_handle;
 

@@ -14,7 +14,7 @@ from . import build as _build
 c_void_p, c_int32, c_double = ctypes.c_void_p, ctypes.c_int32, ctypes.c_double
 
 DS_OK, DS_ERR_ARG, DS_ERR_CUDA, DS_ERR_NO_DEVICE, DS_ERR_INTERNAL = 0, -1, -2, -3, -4
-DS_LOG_DIV, DS_LOG_DIFF = 0, 1
+DS_LOG_DIV, DS_LOG_DIFF, DS_LOG_RCP = 0, 1, 2
 DS_CTRL_PROPORTIONAL, DS_CTRL_GRADIENT = 1, 2
 DS_MAX_AGENTS, DS_MAX_K = 1024, 16
 

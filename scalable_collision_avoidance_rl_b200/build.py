@@ -9,8 +9,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdronestep.so")
 SOURCES = [os.path.join(CSRC, "dronestep_abi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "dronestep_kernels.cuh"), os.path.join(CSRC, "dronestep_policy.cuh"),
-                  os.path.join(os.path.dirname(PKG_DIR), "include", "dronestep.h")]
+DEPS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + \
+       [os.path.join(os.path.dirname(PKG_DIR), "include", "dronestep.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-pthread", "-shared", "-cudart", "shared"]
 
@@ -35,7 +35,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libdronestep.so")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *SOURCES]
+    extra = os.environ.get("DS_NVCC_EXTRA", "").split()      # tuning builds, e.g. -DDS_RO2_MINCTAS=8
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB_PATH, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -6,6 +6,7 @@
 // CUDA device every compute entry fails with DS_ERR_NO_DEVICE.
 #include "../../include/dronestep.h"
 #include "dronestep_kernels.cuh"
+#include "dronestep_rollout2.cuh"
 #include "dronestep_policy.cuh"
 
 #include <algorithm>
@@ -49,6 +50,11 @@ struct ds_handle {
     int ro_inline;            // near-pair evaluation mode of the rollout kernel (see plan_launch)
     size_t ro_smem;
     size_t smem_optin, smem_sm;
+    // warp-per-environment rollout kernel (dronestep_rollout2.cuh): uniform constants, n <= 32, k in 1..3
+    int ro2_ok;
+    ds::Ro2Args ro2;          // everything but .ra is filled at ds_create
+    int ro2_blocks, ro2_threads;
+    size_t ro2_smem;
     // device constants (Real typed unless noted)
     void *d_xF, *d_ds, *d_delta, *d_radius, *d_logds, *d_thr2;
     int *d_clipcnt;
@@ -71,6 +77,57 @@ struct ds_handle {
 };
 
 namespace {
+
+int env_int(const char *name, int dflt);
+
+// The warp-per-environment rollout kernel (dronestep_rollout2.cuh) applies when every agent has the
+// same radius, d_safety and Delta (any scalar-delta configuration of the reference), 0 <= Delta,
+// 0 < d_safety, the pass-1 threshold is finite, k = 2, the 2-column observation, and n is one of
+// the instantiated agent counts.  DS_RO2=0 forces rollout_kernel (A/B runs).
+#define DS_RO2_NS(X) X(5) X(10) X(32)
+template <typename Real, int N> size_t ro2_warp_bytes() { return sizeof(ds::Ro2Warp<Real, N>); }
+template <typename Real, int N> size_t ro2_cta_bytes() { return ds::ro2_align16(sizeof(ds::Ro2Cta<Real, N>)); }
+template <typename Real>
+void plan_rollout2(ds_handle *h, const Real *dsv, const Real *dl, const Real *rd, const Real *lg, const Real *thr2,
+                   const int *clipcnt)
+{
+    const int n = h->n;
+    h->ro2_ok = 0;
+    if (h->k != 2 || !h->simplify || !env_int("DS_RO2", 1)) return;
+    size_t wbytes = 0, cbytes = 0;
+#define DS_X(NN) if (n == NN) { wbytes = ro2_warp_bytes<Real, NN>(); cbytes = ro2_cta_bytes<Real, NN>(); }
+    DS_RO2_NS(DS_X)
+#undef DS_X
+    if (!wbytes) return;
+    for (int i = 1; i < n; ++i)
+        if (dsv[i] != dsv[0] || dl[i] != dl[0] || rd[i] != rd[0] || thr2[i] != thr2[0] || clipcnt[i] != clipcnt[0]) return;
+    if (!(dsv[0] > (Real)0) || !(dl[0] >= (Real)0) || !(rd[0] >= (Real)0) || !std::isfinite((double)thr2[0]) ||
+        !std::isfinite((double)dsv[0]) || !std::isfinite((double)dl[0]))
+        return;
+    if (clipcnt[0] != 0 && clipcnt[0] != n - 1) return;
+    ds::Ro2Args &a = h->ro2;
+    std::memset(&a, 0, sizeof a);
+    a.ds = (double)dsv[0]; a.delta = (double)dl[0]; a.radius = (double)rd[0]; a.log_ds = (double)lg[0];
+    a.inv_ds = (double)((Real)1 / dsv[0]);                   // correctly rounded in Real: the value div_rn(1, ds) gives
+    {   // (sqrt(thr2) + 2e-3)^2 rounded up: margin >> f32 rounding of |coordinates| < 1024
+        const double th = std::sqrt((double)thr2[0]) + 2e-3;
+        float f = (float)(th * th);
+        if (!((double)f >= th * th)) f = std::nextafterf(f, INFINITY);
+        a.thr2f = f;
+    }
+    a.delta_eff = clipcnt[0] != 0 ? (double)INFINITY : (double)dl[0];
+    // one CTA per environment; its warps are the time segments of a call
+    int segs = env_int("DS_RO2_SEGS", ds::kRo2Threads / 32);
+    segs = segs < 1 ? 1 : (segs > ds::kRo2Threads / 32 ? ds::kRo2Threads / 32 : segs);
+    h->ro2_threads = 32 * segs;
+    h->ro2_blocks = h->E;
+    h->ro2_smem = cbytes + (size_t)segs * wbytes;
+    if (h->ro2_smem > h->smem_optin) return;
+    h->ro2_ok = 1;
+    if (env_int("DS_PLAN_DEBUG", 0))
+        std::fprintf(stderr, "[dronestep] n=%d E=%d rollout2 plan: blocks=%d smem=%zu (%zu per warp)\n",
+                     n, h->E, h->ro2_blocks, h->ro2_smem, wbytes);
+}
 
 template <typename Real>
 int upload_consts(ds_handle *h, const ds_config *cfg)
@@ -112,6 +169,7 @@ int upload_consts(ds_handle *h, const ds_config *cfg)
             if (j != i && dsv[i] <= dl[j]) ++cc;            // :328 for a clipped pair, evaluated in Real
         clipcnt[i] = cc;
     }
+    plan_rollout2<Real>(h, dsv.data(), dl.data(), rd.data(), lg.data(), thr2.data(), clipcnt.data());
     DS_CUDA(cudaMalloc(&h->d_xF, sizeof(Real) * 2 * n));
     DS_CUDA(cudaMalloc(&h->d_ds, sizeof(Real) * n));
     DS_CUDA(cudaMalloc(&h->d_delta, sizeof(Real) * n));
@@ -205,8 +263,8 @@ void plan_launch(ds_handle *h)
 int check_params(const ds_params *p)
 {
     if (!p) return fail(DS_ERR_ARG, "ds_params is NULL");
-    if (p->log_mode != DS_LOG_DIV && p->log_mode != DS_LOG_DIFF)
-        return fail(DS_ERR_ARG, "ds_params.log_mode must be DS_LOG_DIV or DS_LOG_DIFF");
+    if (p->log_mode != DS_LOG_DIV && p->log_mode != DS_LOG_DIFF && p->log_mode != DS_LOG_RCP)
+        return fail(DS_ERR_ARG, "ds_params.log_mode must be DS_LOG_DIV, DS_LOG_DIFF or DS_LOG_RCP");
     if (p->max_time_steps < 1) return fail(DS_ERR_ARG, "ds_params.max_time_steps < 1");
     return DS_OK;
 }
@@ -241,12 +299,12 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
 struct Geom { int blocks, threads; size_t smem; };
 
 template <typename KernelT, typename ArgsT>
-int launch(KernelT kernel, const ArgsT &args, const Geom &gm, cudaStream_t st)
+int launch(KernelT kernel, const ArgsT &args, const Geom &gm, cudaStream_t st, int carveout = cudaSharedmemCarveoutMaxShared)
 {
     if (gm.smem > 48 * 1024)
         DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
-    // residency is shared-memory bound for small CTAs: ask for the largest carve-out
-    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // residency is shared-memory bound for small CTAs: ask for the largest carve-out (default)
+    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
     kernel<<<gm.blocks, gm.threads, gm.smem, st>>>(args);
     DS_CUDA(cudaGetLastError());
     return DS_OK;
@@ -298,8 +356,99 @@ int launch_step(ds_handle *h, const ds::StepArgs &a, cudaStream_t st)
     else if (h->ro_NB == 4) { DS_DISPATCH_RO_K(REAL, 256, 4, ARGS, GEOM) }                \
     else { DS_DISPATCH_RO_K(REAL, 256, 0, ARGS, GEOM) }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (no link-time libcuda dependency)
+typedef CUresult (*ds_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+ds_encode_tiled_fn encode_tiled()
+{
+    static ds_encode_tiled_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return (ds_encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+// largest x with sqrt(x) <= tol in Real arithmetic (sqrt is correctly rounded and monotone): the
+// all-at-goal test of drone_env.py:249-251 without the square root, for the prefix passes
+template <typename Real>
+double goal_threshold_sq(double tol_d)
+{
+    const Real tol = (Real)tol_d;
+    if (!(tol >= (Real)0) || !std::isfinite((double)tol)) return -1.0;          // nothing is ever at its goal / not usable
+    Real x = tol * tol;
+    while (std::sqrt(x) > tol) x = std::nextafter(x, (Real)0);
+    for (;;) {
+        const Real nx = std::nextafter(x, (Real)INFINITY);
+        if (!(std::sqrt(nx) <= tol)) break;
+        x = nx;
+    }
+    return (double)x;
+}
+
+template <typename Real, int N>
+int launch_rollout2_n(ds_handle *h, const ds::Ro2Args &a, const CUtensorMap &tm, cudaStream_t st)
+{
+    auto kernel = ds::rollout2_kernel<Real, N, 2>;
+    if (h->ro2_smem > 48 * 1024)
+        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ro2_smem));
+    // the per-warp blocks need ~24 KB per CTA: leave the rest of the 256 KB to L1 (log table, spills)
+    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, env_int("DS_RO2_CARVE", 75)));
+    if (env_int("DS_PLAN_DEBUG", 0)) {
+        int nb = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, h->ro2_threads, h->ro2_smem);
+        std::fprintf(stderr, "[dronestep] rollout2: %d CTAs of %d threads, %zu B smem, %d resident CTAs per SM, act_mode %d\n",
+                     h->ro2_blocks, h->ro2_threads, h->ro2_smem, nb, a.act_mode);
+    }
+    kernel<<<h->ro2_blocks, h->ro2_threads, h->ro2_smem, st>>>(a, tm);
+    DS_CUDA(cudaGetLastError());
+    return DS_OK;
+}
+
+int launch_rollout2(ds_handle *h, const ds::RolloutArgs &ra, cudaStream_t st)
+{
+    ds::Ro2Args a = h->ro2;
+    a.ra = ra;
+    a.goal_t2 = h->real_bytes == 8 ? goal_threshold_sq<double>(ra.s.goal_tol) : goal_threshold_sq<float>(ra.s.goal_tol);
+    if (a.goal_t2 < 0 && !(ra.s.goal_tol >= 0)) a.goal_t2 = -1.0;
+    // TMA: 16-byte aligned source, slice blocks a multiple of 16 bytes.  2: one 2-D tile per chunk
+    // (tensor map over [T][E * n * 2] Reals); 1: one 1-D bulk copy per slice; 0: per-lane loads.
+    const size_t rb = (size_t)h->real_bytes, blk = (size_t)h->n * 2 * rb;
+    const int want = env_int("DS_RO2_ACT", 2);
+    a.act_mode = 0;
+    CUtensorMap tm;
+    std::memset(&tm, 0, sizeof tm);
+    if (ra.actions && blk % 16 == 0 && ((uintptr_t)ra.actions % 16) == 0 && want > 0) {
+        a.act_mode = 1;
+        ds_encode_tiled_fn enc = want >= 2 ? encode_tiled() : nullptr;
+        if (enc) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)h->E * h->n * 2, (cuuint64_t)ra.T};
+            const cuuint64_t gstr[1] = {(cuuint64_t)h->E * h->n * 2 * rb};
+            const cuuint32_t box[2] = {(cuuint32_t)h->n * 2, (cuuint32_t)(32 / h->n)};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult rc = enc(&tm, rb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                    const_cast<void *>(ra.actions), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc == CUDA_SUCCESS) a.act_mode = 2;
+        }
+    }
+#define DS_X(NN)                                                                                   \
+    if (h->n == NN)                                                                                \
+        return h->real_bytes == 8 ? launch_rollout2_n<double, NN>(h, a, tm, st) : launch_rollout2_n<float, NN>(h, a, tm, st);
+    DS_RO2_NS(DS_X)
+#undef DS_X
+    return fail(DS_ERR_INTERNAL, "rollout2: no instantiation for this n");
+}
+
 int launch_rollout(ds_handle *h, const ds::RolloutArgs &a, cudaStream_t st)
 {
+    if (h->ro2_ok) return launch_rollout2(h, a, st);
     const Geom gm{h->ro_blocks, h->ro_threads, h->ro_smem};
     if (h->real_bytes == 8) { DS_DISPATCH_RO(double, a, gm) }
     else { DS_DISPATCH_RO(float, a, gm) }

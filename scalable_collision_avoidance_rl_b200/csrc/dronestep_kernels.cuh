@@ -143,11 +143,17 @@ DS_HD double bits_double(long long b)
     double a; memcpy(&a, &b, sizeof a); return a;
 #endif
 }
+// (out of line: libm's log is ~200 instructions that the callers' hot loops should not carry)
+#if DS_DEVICE_CODE
+__device__ __noinline__ double log_unusual(double x) { return log(x); }
+#else
+inline double log_unusual(double x) { return log(x); }
+#endif
 DS_HD double log_r(double x, const LogTabEntry *__restrict__ tab)
 {
     const long long b = double_bits(x);
     const int hi = (int)(b >> 32);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log_unusual(x);
     const int hs = hi + kLogTabOffset;
     const int e = (hs >> 20) - 1023;
     const LogTabEntry t = tab[(hs >> 13) & (kLogTabSize - 1)];
@@ -356,9 +362,14 @@ DS_HD void eval_pair(PairOut<Real> &po, Real xi, Real yi, Real xj, Real yj, Real
         const Real dn = div_rn(ds_i, d);
         coll = dn <= (Real)0;
         lg = log_r((live && !coll) ? dn : (Real)1, tab);
-    } else {
+    } else if (P.log_mode == 1) {
         coll = (ds_i > (Real)0) ? (d < (Real)0) : (ds_i == (Real)0);
         lg = sub_rn(log_ds_i, log_r((live && !coll) ? fabs(d) : fabs(ds_i), tab));
+    } else {
+        // DS_LOG_RCP: log(d_safety / d) = -log(d * (1 / d_safety)); the reciprocal is rounded once
+        // (the rollout kernels get it precomputed; same value)
+        coll = (ds_i > (Real)0) ? (d < (Real)0) : (ds_i == (Real)0);
+        lg = -log_r((live && !coll) ? mul_rn(d, div_rn((Real)1, ds_i)) : (Real)1, tab);
     }
     po.coll = live && coll;
     po.logd = live ? (coll ? P.sentinel : lg) : (Real)0;

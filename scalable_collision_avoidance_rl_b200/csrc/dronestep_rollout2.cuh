@@ -1,0 +1,689 @@
+// dronestep_rollout2.cuh -- warp-per-environment rollout kernel (the benchmarked kernel of round 2).
+//
+// Same observable behaviour as rollout_kernel (dronestep_kernels.cuh): T fused steps of
+// drones.step() (reference drone_env.py:214-258) per environment, every per-step output recorded,
+// early termination (drone_env.py:248-256), finished codes, done flags, episode sums.  Different
+// decomposition, chosen after the round-1 profile showed the CTA-wide version bound by instruction
+// issue (58 % issue slots, 1.07 barrier-stall cycles per issue, 1410 warp-instructions per 32
+// agent-steps of which only ~12 % were fp64 arithmetic):
+//
+//   * ONE WARP owns ONE environment for the whole call and walks its episode in chunks of
+//     TCW = floor(32 / N) consecutive time slices: lane = (slice s, agent i), one row of the pair
+//     matrix per lane.  Nothing is shared between warps but the per-CTA constants, so the chunk
+//     loop has NO CTA barrier -- only __syncwarp between its phases.
+//   * N (agents) is a template parameter: slice / agent of a lane, trip counts, shared-memory
+//     offsets are compile-time; the phases are written as straight-line predicated code with
+//     warp-uniform loop bounds (no divergent branches in the chunk loop's hot phases).
+//   * The episode's action stream is moved by the TMA unit: per chunk one cp.async.bulk
+//     (global -> shared, mbarrier complete_tx) per time slice brings that slice's contiguous
+//     [N][2] block into a 3-deep ring, two chunks ahead of its use; no thread holds an action in
+//     a register while it waits.  A lane-load form remains for index mode / unaligned blocks.
+//   * Every agent has the same radius, d_safety and Delta in every configuration the reference
+//     can construct with a scalar delta (drone_env.py:75,85-91,153 on a circle formation), and
+//     then d_ij, log(d_safety/d_ij), the collision test and the Delta-disk test are symmetric in
+//     (i, j): each UNORDERED near pair is evaluated once (one sqrt / log instead of two) and its
+//     result is scattered to the result segments of both rows.  Non-uniform constants, other n,
+//     k != 2 and the 5-column observation take rollout_kernel (the host decides per handle).
+//   * A row folds its segment in ascending j (sums; k nearest with strict "<" insertion = stable
+//     argsort order); collision counts are posted by the pair lanes (rare), the Delta-disk count
+//     follows from the k nearest (uniform Delta), so the fold loop carries only what needs order.
+//   * Frames too dense for the list (more near pairs than its capacity) are evaluated in groups
+//     of rows, every pair of a group's rows exactly, through the same fold -- correct for any
+//     density, never taken at the BASELINE densities.
+//
+// The arithmetic (operation order of eval_pair / row_end / write_obs) is that of
+// dronestep_kernels.cuh, so this kernel, rollout_kernel and step_kernel agree bit for bit.
+#pragma once
+#include <cuda.h>      // CUtensorMap (type only; the encoder is resolved at run time by the host side)
+#include "dronestep_kernels.cuh"
+
+namespace ds {
+
+#if defined(__CUDACC__)
+
+struct Ro2Args {
+    RolloutArgs ra;
+    // uniform per-agent constants
+    double ds, delta, radius, log_ds, inv_ds;
+    double delta_eff;       // Delta, or +inf when d_safety <= Delta (every agent is inside every Delta disk)
+    double goal_t2;         // largest x with sqrt_rn(x) <= goal_tol: the goal test without the square root
+    float thr2f;            // pass-1 threshold of the packed-f32 filter (squared, with margin)
+    int act_mode;           // action staging: 0 lane loads, 1 cp.async.bulk per slice, 2 one 2-D TMA tile per chunk
+};
+
+constexpr int kRo2Stages = 3;       // action ring depth (chunks)
+constexpr int kRo2Threads = 128;    // 4 warps = 4 time segments of one environment per CTA
+constexpr int kRo2MaxSeg = 8;
+#ifndef DS_RO2_MINCTAS
+#define DS_RO2_MINCTAS 6            // 24 warps per SM: 80 registers per thread (72 spills 50 B, 64 spills 130 B)
+#endif
+
+__host__ __device__ inline size_t ro2_align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+// Per-warp shared memory (compile-time layout).
+template <typename Real, int N> struct alignas(128) Ro2Warp {
+    using V2 = typename vec2_of<Real>::type;
+    static constexpr int TCW = 32 / N, RW = TCW * N, HP = (N + 1) / 2;
+    static constexpr int LW = (RW * (N - 1) < 128) ? RW * (N - 1) : 128;          // ordered result slots
+    static constexpr int LU = (RW * (N - 1) / 2 < 64) ? RW * (N - 1) / 2 : 64;    // unordered list entries
+    static constexpr int GR = LW / (N - 1);                                       // rows per group, dense mode
+    static constexpr int ASTR = (int)(((RW * sizeof(V2) + 127) / 128) * 128 / sizeof(V2));   // stage stride: 128-byte aligned (TMA)
+    V2 act[kRo2Stages][ASTR]; // action ring: [slice][agent] of a chunk, as in global memory
+    V2 pos[32];               // positions of the chunk's rows (row = lane)
+    V2 pend[32];              // agent's position after the previous chunk (lane (s, i): agent i; same in every s)
+    V2 acc[32];               // running episode sums (r, true_r) of the lane's rows
+    int sumc[32];             // running collision count of the slice's frames (lanes with i == 0)
+    V2 res[LW];               // (d, log term) per ordered near pair, row-contiguous, ascending j
+    float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
+    uint2 rowinfo[32];        // (near mask, first result slot) of each row
+    unsigned ent[LU];         // unordered near pairs
+    unsigned umask[32];       // near AND not clipped (pair lanes clear the rare clipped-near bits)
+    int cnt[32];              // collision count per frame (slice)
+    unsigned long long mbar[kRo2Stages];
+};
+
+__device__ __forceinline__ unsigned ro2_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ro2_mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ro2_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ro2_mbar_expect(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ro2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy (1-D, no tensor map) global -> shared; the bytes are counted on the mbarrier
+__device__ __forceinline__ void ro2_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ro2_smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(ro2_smem_u32(bar)) : "memory");
+}
+// TMA tile load (2-D tensor map over the action stream: rows = time steps, row = [E][N][2] Reals):
+// one instruction brings the [TCW][N][2] block of a chunk; rows beyond T are zero-filled and counted
+__device__ __forceinline__ void ro2_tma_g2s_2d(void *dst, const void *tmap, int x, int y, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     ro2_smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(ro2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ro2_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned addr = ro2_smem_u32(bar);
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();                  // a lost copy must fail loudly, not hang the device
+    }
+}
+
+// distance_data() for one pair when radius, d_safety and Delta are the same for every agent
+// (drone_env.py:314-332): the result holds for (i, j) and (j, i).  Operation order of eval_pair;
+// log_mode 2 replaces the division by a multiplication with the rounded reciprocal of d_safety:
+// log(d_safety / d) = -log(d * (1 / d_safety)),  <= 3.4e-16 absolute difference.
+template <typename Real>
+__device__ __forceinline__ void ro2_eval_pair(Real &d_out, Real &logd_out, bool &coll_out, Real xi, Real yi, Real xj,
+                                              Real yj, Real ds, Real rad, Real log_ds, Real inv_ds, int log_mode,
+                                              Real zero_eps, Real sentinel, const LogTabEntry *__restrict__ tab)
+{
+    const Real dx = sub_rn(xi, xj), dy = sub_rn(yi, yj);
+    const Real dist = sqrt_rn(fma_rn(dy, dy, mul_rn(dx, dx)));     // :318 (BLAS ddot)
+    const Real raw = sub_rn(sub_rn(dist, rad), rad);               // :318
+    Real d = (ds < raw) ? ds : raw;                                // python min(raw, d_safety[i])
+    d = (d == (Real)0) ? zero_eps : d;                             // :319-320
+    const bool live = d != ds;
+    // one table-driven log; its argument and the use of its value depend on the mode
+    bool coll;
+    Real x;
+    if (log_mode == 0) {
+        x = div_rn(ds, d);
+        coll = x <= (Real)0;
+    } else {
+        coll = d < (Real)0;                                        // d_safety > 0 on this path
+        x = (log_mode == 1) ? fabs(d) : mul_rn(d, inv_ds);
+    }
+    const Real one = (log_mode == 1) ? fabs(ds) : (Real)1;
+    Real lg = log_r((live && !coll) ? x : one, tab);
+    lg = (log_mode == 0) ? lg : ((log_mode == 1) ? sub_rn(log_ds, lg) : -lg);
+    d_out = d;
+    coll_out = live && coll;
+    logd_out = live ? (coll ? sentinel : lg) : (Real)0;
+}
+
+// Pass 1 over the N agents of the row's frame on the packed-f32 pipe (see pass1_block_f32x2).
+template <int N>
+__device__ __forceinline__ unsigned ro2_pass1(const float4 *__restrict__ fp, float nx, float ny, float thr2f)
+{
+    constexpr int HP = (N + 1) / 2;
+    const float2 NX = make_float2(nx, nx), NY = make_float2(ny, ny);
+    const float2 TH = make_float2(thr2f, thr2f), M1 = make_float2(-1.0f, -1.0f);
+    unsigned m = 0;
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+        const float4 pq = fp[q];
+        const float2 a = __fadd2_rn(make_float2(pq.x, pq.y), NX);
+        const float2 b = __fadd2_rn(make_float2(pq.z, pq.w), NY);
+        const float2 t = __ffma2_rn(__ffma2_rn(b, b, __fmul2_rn(a, a)), M1, TH);   // thr2 - d2
+        m = __funnelshift_l(__float_as_uint(t.x), m, 1);
+        m = __funnelshift_l(__float_as_uint(t.y), m, 1);
+    }
+    // m: NOT-near bits of 2 HP agents, agent jj at bit 2 HP - 1 - jj (a pad agent sits at 1e30: not near)
+    m = __brev(~m) >> (32 - 2 * HP);
+    return (N < 32) ? (m & ((1u << N) - 1u)) : m;
+}
+
+// Fold of a row's result segment in ascending j: sums (:282-283) and the K nearest partners
+// (strict "<": equal distances stay in index order).  Warp-uniform trip count; lanes with fewer
+// partners fold (d_safety, +0) -- never a candidate, adds nothing -- in the tail.
+template <typename Real, int K>
+__device__ __forceinline__ void ro2_fold(const typename vec2_of<Real>::type *__restrict__ rp, unsigned mm, Real ds, Real delta_eff,
+                                         Real &sum_all, Real &sum_loc, Real (&nd)[K], int (&nj)[K])
+{
+    using V2 = typename vec2_of<Real>::type;
+    const int iters = __reduce_max_sync(0xffffffffu, __popc(mm));
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const bool on = mm != 0;
+        const int j = __ffs((int)mm) - 1;
+        mm &= mm - 1;
+        V2 dv; dv.x = ds; dv.y = 0;
+        if (on) { dv = *rp; ++rp; }
+        sum_all = add_rn(sum_all, dv.y);                                                       // :283
+        sum_loc = add_rn(sum_loc, mul_rn(dv.y, (dv.x <= delta_eff) ? (Real)1 : (Real)0));      // :282
+        bool lt[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) lt[q] = dv.x < nd[q];           // false for NaN; clipped (== d_safety) never enters
+#pragma unroll
+        for (int q = K - 1; q > 0; --q) {
+            nd[q] = lt[q - 1] ? nd[q - 1] : (lt[q] ? dv.x : nd[q]);
+            nj[q] = lt[q - 1] ? nj[q - 1] : (lt[q] ? j : nj[q]);
+        }
+        nd[0] = lt[0] ? dv.x : nd[0];
+        nj[0] = lt[0] ? j : nj[0];
+    }
+}
+
+// -np.nan_to_num(v) (drone_env.py:287-288); the rewards are finite unless a position is not
+DS_HD double ro2_neg_nan_to_num(double v)
+{
+    if (!(fabs(v) <= 1.7976931348623157e308)) v = nan_to_num(v);
+    return -v;
+}
+DS_HD float ro2_neg_nan_to_num(float v)
+{
+    if (!(fabsf(v) <= 3.4028234663852886e38f)) v = nan_to_num(v);
+    return -v;
+}
+
+// Shared memory of a CTA in front of its per-warp blocks: constants and the segments' episode sums.
+template <typename Real, int N> struct alignas(128) Ro2Cta {
+    using V2 = typename vec2_of<Real>::type;
+    V2 cF[N];                          // end points
+    double part[kRo2MaxSeg][4];        // per-segment episode sums: r, true_r, collisions, steps
+    int seg_fin[kRo2MaxSeg];           // the episode ended inside this segment
+    LogTabEntry logtab[sizeof(Real) == 8 ? kLogTabSize : 1];
+};
+
+template <typename Real, int N, int K>
+__global__ void __launch_bounds__(kRo2Threads, DS_RO2_MINCTAS)
+rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
+{
+    using V2 = typename vec2_of<Real>::type;
+    using WS = Ro2Warp<Real, N>;
+    using CS = Ro2Cta<Real, N>;
+    constexpr int TCW = WS::TCW, RW = WS::RW, HP = WS::HP;
+    constexpr unsigned fullN = (N >= 32) ? 0xffffffffu : ((1u << N) - 1u);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const RolloutArgs &ra = A.ra;
+    const StepArgs &a = ra.s;
+    const int E = a.E, T = ra.T;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (opaque to the optimiser: otherwise every use of a per-warp address re-derives them from %tid)
+    asm volatile("" : "+r"(lane), "+r"(warp));
+    const int S = blockDim.x >> 5;
+    const int e = blockIdx.x;                                    // one environment per CTA, one time segment per warp
+
+    // ---- per-CTA constants: end points, log table
+    CS &C = *reinterpret_cast<CS *>(smem_raw);
+    const LogTabEntry *logtab = C.logtab;
+    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) C.cF[idx] = reinterpret_cast<const V2 *>(a.c.xF)[idx];
+    if (sizeof(Real) == 8)
+        for (int idx = threadIdx.x; idx < kLogTabSize; idx += blockDim.x) C.logtab[idx] = a.c.logtab[idx];
+    WS &W = *reinterpret_cast<WS *>(smem_raw + sizeof(CS) + (size_t)warp * sizeof(WS));
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kRo2Stages; ++st) ro2_mbar_init(&W.mbar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    W.cnt[lane] = 0;
+    __syncthreads();
+
+    const int s = lane / N, i = lane - s * N;                    // slice in the chunk, agent
+    const bool rowlane = lane < RW;
+    const unsigned EN = (unsigned)E * N;
+    const unsigned g = (unsigned)e * N + (rowlane ? i : 0);
+    const Real ds = (Real)A.ds, rad = (Real)A.radius, delta_eff = (Real)A.delta_eff;
+    const int act_mode = A.act_mode;
+    const bool direct = ra.actions != nullptr;
+    const V2 *atab = reinterpret_cast<const V2 *>(ra.atable);
+
+    // ---- the call's time axis is cut into S segments of whole chunks; warp k owns segment k
+    const int nchunks = (T + TCW - 1) / TCW;
+    const int Cs = (nchunks + S - 1) / S;                        // chunks per segment
+    const int c0 = warp * Cs, c1 = (c0 + Cs < nchunks) ? c0 + Cs : nchunks;
+    const int ta = c0 * TCW, Tend = (c1 * TCW < T) ? c1 * TCW : T;   // steps [ta, Tend) of the call
+    const bool alive0 = ra.done[e] == 0;
+    const int tenv0 = a.t[e];
+    int tlim = a.max_steps - 1 - tenv0;                          // step of the call at which the time limit ends the episode
+    tlim = tlim < 0 ? 0 : tlim;
+
+    auto load_lane = [&](int c) -> V2 {                          // action of row (s, i) of chunk c
+        V2 u{};
+        const int t = c * TCW + s;
+        if (rowlane && t < T) {
+            const size_t at = (size_t)t * EN + g;
+            u = direct ? reinterpret_cast<const V2 *>(ra.actions)[at] : atab[ra.aidx[at]];
+        }
+        return u;
+    };
+    // one chunk of sequential, bit-exact single-integrator steps of agent i (A = I, B = dt I,
+    // drone_env.py:78-79,235) from the staged actions ua[q * N]; lane (s, i) keeps slice s
+    const Real dt = (Real)a.dt;
+    auto integrate = [&](const V2 *ua, V2 &pend, V2 &pm) {
+#pragma unroll
+        for (int q = 0; q < TCW; ++q) {
+            const V2 u = ua[q * N];
+            pend.x = add_rn(pend.x, mul_rn(dt, u.x));
+            pend.y = add_rn(pend.y, mul_rn(dt, u.y));
+            if (q == s) pm = pend;
+        }
+    };
+
+    // ---- prefix: the state at the start of this warp's segment.  Only the integrator runs over the
+    // steps in front of it (two dependent fp64 operations per step; actions fetched eight chunks
+    // ahead), with the episode-end test of the main loop: a segment behind the end does nothing.
+    int tstar = 0x7fffffff;                                     // first step at which every agent is at its goal
+    {
+        V2 pend{};                                              // agent i's position after the previous chunk
+        if (rowlane && alive0) pend = reinterpret_cast<const V2 *>(a.pos)[g];
+    if (alive0 && c0 > 0 && c0 < nchunks && tlim >= ta) {
+        V2 pm{};
+        const V2 xF = C.cF[i];
+        for (int cb = 0; cb < c0 && tstar == 0x7fffffff; cb += 8) {
+            V2 u8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u8[q] = load_lane(cb + q);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = cb + q;
+                if (c < c0) {                                    // warp-uniform
+                    V2 *buf = &W.act[q & 1][0];
+                    if (rowlane) buf[lane] = u8[q];
+                    __syncwarp();
+                    integrate(buf + i, pend, pm);
+                    // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
+                    const Real gx = sub_rn(xF.x, pm.x), gy = sub_rn(xF.y, pm.y);
+                    const bool atg = rowlane && add_rn(mul_rn(gx, gx), mul_rn(gy, gy)) <= (Real)A.goal_t2;
+                    const unsigned gbal = __ballot_sync(0xffffffffu, atg);
+                    const bool slice_goal = rowlane && i == 0 && (((gbal >> (lane & 31)) & fullN) == fullN);
+                    const unsigned sbal = __ballot_sync(0xffffffffu, slice_goal);
+                    if (sbal && tstar == 0x7fffffff) tstar = c * TCW + (__ffs((int)sbal) - 1) / N;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring is next written by TMA copies
+        __syncwarp();
+    }
+        W.pend[lane] = pend;
+        V2 z2; z2.x = 0; z2.y = 0;
+        W.acc[lane] = z2;
+        W.sumc[lane] = 0;
+    }
+
+    // ---- this warp's segment
+    const int tfin_pre = (tstar < tlim) ? tstar : tlim;          // last executed step, as far as known in front of the segment
+    const bool dead = !alive0 || T <= 0 || c0 >= nchunks || tfin_pre < ta;
+    int steps = 0;
+    if (lane == 0)
+        W.cnt[31] = (int)((ra.pos_tr ? 1u : 0u) | (ra.vel_tr ? 2u : 0u) | (ra.r_tr ? 4u : 0u) | (ra.tr_tr ? 8u : 0u) |
+                          (ra.z_tr ? 16u : 0u) | (ra.ncoll_tr ? 32u : 0u) | (ra.fin_tr ? 64u : 0u));   // record mask (slot 31 is never a frame count: TCW <= 32 only for N = 1)
+
+    // ---- action staging.  TMA: lane 0 brings chunk c's [TCW][N][2] block into ring stage (c - c0) % 3
+    // (one 2-D tile, or one 1-D bulk copy per slice); lane-load form: every row lane holds the action
+    // of its row one chunk ahead.
+    auto issue_tma = [&](int c, int st) {                        // lane 0 only
+        constexpr unsigned blk = (unsigned)N * (unsigned)sizeof(V2);
+        if (act_mode == 2) {
+            ro2_mbar_expect(&W.mbar[st], (unsigned)TCW * blk);
+            ro2_tma_g2s_2d(&W.act[st][0], &tmap, e * N * 2, c * TCW, &W.mbar[st]);
+        } else {
+            const int t0c = c * TCW;
+            const int nslc = (T - t0c < TCW) ? (T - t0c) : TCW;
+            ro2_mbar_expect(&W.mbar[st], (unsigned)nslc * blk);
+            const V2 *src = reinterpret_cast<const V2 *>(ra.actions) + ((size_t)t0c * EN + (size_t)e * N);
+#pragma unroll 1
+            for (int q = 0; q < nslc; ++q) ro2_bulk_g2s(&W.act[st][q * N], src + (size_t)q * EN, blk, &W.mbar[st]);
+        }
+    };
+    V2 upre{};
+    if (!dead) {
+        if (act_mode) {
+            if (lane == 0) {
+                issue_tma(c0, 0);
+                if (c0 + 1 < c1) issue_tma(c0 + 1, 1);
+            }
+        } else {
+            if (rowlane) W.act[0][lane] = load_lane(c0);
+            upre = load_lane(c0 + 1);
+        }
+    }
+    __syncwarp();
+
+    // state of the last processed chunk, read by the epilogue after the loop
+    V2 ui{}, zrow[K + 1];
+    int nirow[K + 1];
+    Real r_i = 0, tr_i = 0;
+    int ne = 0, nc = 0;
+    bool env_fin = false;
+    int t0 = ta;
+
+    int st = 0;                                                  // ring stage of the current chunk
+    unsigned par = 0;                                            // mbarrier phase parity of that stage's current use
+    unsigned at = (unsigned)(ta + s) * EN + g;                   // element index of this row at slice t0 + s
+    for (int c = dead ? c1 : c0; c < c1; ++c, t0 += TCW, at += (unsigned)TCW * EN) {
+        const bool in_chunk = rowlane && (t0 + s < T);
+        const V2 *uact = &W.act[st][0];
+        // ---- next-but-one chunk's actions on their way; this chunk's have landed
+        if (act_mode) {
+            if (lane == 0 && c + 2 < c1) {
+                int st2 = st + 2; st2 = st2 >= kRo2Stages ? st2 - kRo2Stages : st2;
+                issue_tma(c + 2, st2);                           // the stage last read in chunk c - 1
+            }
+            ro2_mbar_wait(&W.mbar[st], par);
+        }
+        float fx, fy;
+        {
+            V2 pend = W.pend[lane], pm{};
+            integrate(uact + i, pend, pm);
+            W.pend[lane] = pend;
+            // f32 copy for pass 1: component (i & 1) of x / y in float4 (i >> 1) of frame s
+            const bool okf = fabs(pm.x) < (Real)1024 && fabs(pm.y) < (Real)1024;   // false for NaN / inf too
+            fx = okf ? (float)pm.x : __int_as_float(0x7fc00000);
+            fy = okf ? (float)pm.y : __int_as_float(0x7fc00000);
+            W.pos[lane] = pm;
+        }
+        if (rowlane) {
+            float *pfa = reinterpret_cast<float *>(&W.posf[s * HP + (i >> 1)]) + (i & 1);
+            pfa[0] = fx; pfa[2] = fy;
+            if ((N & 1) && i == N - 1) { pfa[1] = 1e30f; pfa[3] = 1e30f; }      // odd N: the missing partner never is near
+        }
+        __syncwarp();
+
+        // ---- pass 1 (packed f32): near mask of the row
+        unsigned m = ro2_pass1<N>(&W.posf[(rowlane ? s : 0) * HP], -fx, -fy, A.thr2f) & ~(1u << i);
+        m = in_chunk ? m : 0u;
+        const unsigned mU = m & (0xfffffffeu << i);              // partners above i
+        const int cFl = __popc(m), cUl = __popc(mU);
+        int incl = cUl | (cFl << 16);                            // both counts in one scan
+#pragma unroll
+        for (int w = 1; w < 32; w <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, w);
+            incl += (lane >= w) ? v : 0;
+        }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        const int totU = tot & 0xffff, totF = tot >> 16;
+        const int baseF = (incl >> 16) - cFl;
+        Real sum_all = 0, sum_loc = 0, nd[K];
+        int nj[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) { nd[q] = ds; nj[q] = -1; }
+        if (totU <= WS::LU && totF <= WS::LW) {                  // warp-uniform
+            // ---- list of the UNORDERED near pairs (j > i)
+            {
+                W.rowinfo[lane] = make_uint2(m, (unsigned)baseF);
+                W.umask[lane] = m;
+                unsigned *ep = W.ent + ((incl & 0xffff) - cUl);
+                unsigned mm = mU;
+                // slot of (i, j) in row i's segment: its rank among the row's near partners
+                unsigned ew = (unsigned)lane | ((unsigned)i << 5) |
+                              (((unsigned)baseF + (unsigned)__popc(m & ((1u << i) - 1u))) << 15);
+                const int iters = __reduce_max_sync(0xffffffffu, cUl);
+#pragma unroll 1
+                for (int it = 0; it < iters; ++it) {
+                    if (mm) {
+                        const int j = lowest_bit(mm);
+                        mm &= mm - 1;
+                        *ep++ = ew | ((unsigned)j << 10);
+                        ew += 1u << 15;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- pass 2: one unordered near pair per lane per round; result to both rows' segments
+#pragma unroll 1
+            for (int q0 = 0; q0 < totU; q0 += 32) {
+                const int q = q0 + lane;
+                const bool valid = q < totU;
+                const unsigned w = W.ent[valid ? q : 0];
+                const int ri = (int)(w & 31u), ii = (int)((w >> 5) & 31u), j = (int)((w >> 10) & 31u);
+                const int rj = ri - ii + j;
+                const unsigned slot_i = w >> 15;
+                const uint2 inf_j = W.rowinfo[rj];
+                const unsigned slot_j = inf_j.y + (unsigned)__popc(inf_j.x & ((1u << ii) - 1u));
+                const V2 pi = W.pos[ri], pj = W.pos[rj];
+                V2 dv;
+                bool coll;
+                ro2_eval_pair<Real>(dv.x, dv.y, coll, pi.x, pi.y, pj.x, pj.y, ds, rad, (Real)A.log_ds, (Real)A.inv_ds,
+                                    a.log_mode, (Real)a.zero_eps, (Real)a.sentinel, logtab);
+                if (valid) {
+                    W.res[slot_i] = dv;
+                    W.res[slot_j] = dv;
+                    if (coll) atomicAdd(&W.cnt[(ri - ii) / N], 2);                // both ordered pairs collide (:284,327)
+                    if (!(dv.x != ds)) {                                          // near but clipped (inside the f32 margin)
+                        atomicAnd(&W.umask[ri], ~(1u << j));
+                        atomicAnd(&W.umask[rj], ~(1u << ii));
+                    }
+                }
+            }
+            __syncwarp();
+            ro2_fold<Real, K>(W.res + baseF, m, ds, delta_eff, sum_all, sum_loc, nd, nj);
+        } else {
+            // ---- dense frames: groups of GR rows, every pair of a group's rows evaluated exactly
+            W.umask[lane] = fullN & ~(1u << i);
+            __syncwarp();
+#pragma unroll 1
+            for (int gs = 0; gs < RW; gs += WS::GR) {
+#pragma unroll 1
+                for (int q0 = 0; q0 < WS::GR * (N - 1); q0 += 32) {
+                    const int q = q0 + lane;
+                    const int rr = q / (N - 1), jj = q - rr * (N - 1);
+                    const int row = gs + rr, sr = row / N, ir = row - sr * N;
+                    const bool valid = q < WS::GR * (N - 1) && row < RW && (t0 + sr < T);
+                    const int j = jj + (jj >= ir ? 1 : 0);
+                    const int rowc = valid ? row : 0, rjc = valid ? row - ir + j : 0;
+                    const V2 pi = W.pos[rowc], pj = W.pos[rjc];
+                    V2 dv;
+                    bool coll;
+                    ro2_eval_pair<Real>(dv.x, dv.y, coll, pi.x, pi.y, pj.x, pj.y, ds, rad, (Real)A.log_ds, (Real)A.inv_ds,
+                                        a.log_mode, (Real)a.zero_eps, (Real)a.sentinel, logtab);
+                    if (valid) {
+                        W.res[q] = dv;
+                        if (coll) atomicAdd(&W.cnt[sr], 1);
+                        if (!(dv.x != ds)) atomicAnd(&W.umask[row], ~(1u << j));
+                    }
+                }
+                __syncwarp();
+                const bool mine = in_chunk && lane >= gs && lane < gs + WS::GR;
+                ro2_fold<Real, K>(W.res + (mine ? (lane - gs) * (N - 1) : 0), mine ? (fullN & ~(1u << i)) : 0u, ds, delta_eff,
+                                  sum_all, sum_loc, nd, nj);
+                __syncwarp();
+            }
+        }
+        // ---- the row: k nearest, goal cost, rewards, observation (all lanes; stores predicated)
+        {
+            // free slots <- lowest clipped indices (all tie at exactly d_safety: index order)
+            unsigned cm = ~(W.umask[lane] | (1u << i));
+            if (N < 32) cm &= (1u << N) - 1u;
+#pragma unroll
+            for (int q = 0; q < K; ++q) {
+                const bool take = nj[q] < 0 && cm != 0;
+                nj[q] = take ? (__ffs((int)cm) - 1) : nj[q];
+                cm = take ? (cm & (cm - 1)) : cm;
+            }
+            // Delta-disk count, capped at k: the in-disk partners are the nearest ones (uniform Delta)
+            int inr = 0;
+#pragma unroll
+            for (int q = 0; q < K; ++q) inr += (nj[q] >= 0 && nd[q] <= delta_eff) ? 1 : 0;
+            // the row's own entry (:323-325) precedes every partner unless one coincides with the agent
+            // (d_ij == d_ii) and has a lower index: merge with the (d, j) rule
+            const Real raw_ii = sub_rn(sub_rn((Real)0, rad), rad);
+            const Real d_ii = (ds < raw_ii) ? ds : raw_ii;
+            if (nj[0] >= 0 && nd[0] <= d_ii) {                              // coincident agents only
+                int pself = 0;
+#pragma unroll
+                for (int q = 0; q < K; ++q)
+                    pself += (nj[q] >= 0 && (nd[q] < d_ii || (nd[q] == d_ii && nj[q] < i))) ? 1 : 0;
+                int mj[K];
+#pragma unroll
+                for (int kth = 1; kth <= K; ++kth)
+                    mj[kth - 1] = (kth < pself) ? nj[kth < K ? kth : K - 1] : ((kth == pself) ? i : nj[kth - 1]);
+#pragma unroll
+                for (int q = 0; q < K; ++q) nj[q] = mj[q];
+            }
+            // goal cost, rewards, termination flag (:249-251,272-288)
+            const V2 pm = W.pos[lane], xF = C.cF[i];
+            const Real gx = sub_rn(xF.x, pm.x), gy = sub_rn(xF.y, pm.y);
+            const Real nrm = sqrt_rn(add_rn(mul_rn(gx, gx), mul_rn(gy, gy)));     // :249,276 (axis norm, unfused)
+            const Real goal = mul_rn((Real)a.q, mul_rn(nrm, nrm));                // :276
+            r_i = ro2_neg_nan_to_num(add_rn(goal, mul_rn((Real)a.b, sum_loc)));   // :282,287
+            tr_i = ro2_neg_nan_to_num(add_rn(goal, mul_rn((Real)a.b, sum_all)));  // :283,288
+            const bool at_goal = nrm <= (Real)a.goal_tol;
+            // observation (:344-397): own row, then the k nearest inside Delta or ghosts
+            zrow[0].x = -gx; zrow[0].y = -gy;                                     // :357
+            Real ghx = 0, ghy = 0;
+            if (inr < K) {                                                        // ghost rows (:383-386)
+                const Real zn = sqrt_rn(fma_rn(gy, gy, mul_rn(gx, gx)));
+                ghx = mul_rn(mul_rn(div_rn(-gx, zn), (Real)A.delta), (Real)a.ghost);
+                ghy = mul_rn(mul_rn(div_rn(-gy, zn), (Real)A.delta), (Real)a.ghost);
+            }
+            nirow[0] = i;
+            const V2 *fpos = &W.pos[lane - i];
+#pragma unroll
+            for (int kth = 1; kth <= K; ++kth) {
+                const int j = nj[kth - 1] < 0 ? 0 : nj[kth - 1];
+                const bool in_r = kth <= inr;                                     // :362-368
+                const V2 pj = fpos[rowlane ? j : 0];
+                zrow[kth].x = in_r ? sub_rn(pj.x, pm.x) : ghx;
+                zrow[kth].y = in_r ? sub_rn(pj.y, pm.y) : ghy;
+                nirow[kth] = in_r ? j : -1;
+            }
+            // ---- which slices execute (drone_env.py:248-256)
+            const unsigned gbal = __ballot_sync(0xffffffffu, in_chunk && at_goal);
+            const bool slice_goal = in_chunk && i == 0 && (((gbal >> (lane & 31)) & fullN) == fullN);
+            const unsigned sbal = __ballot_sync(0xffffffffu, slice_goal);
+            const int nsl = (T - t0 < TCW) ? (T - t0) : TCW;     // slices in this chunk
+            const int fg = sbal ? lowest_bit(sbal) / N : nsl;    // first slice with everybody at goal
+            int ft = a.max_steps - 1 - (tenv0 + t0);             // first slice at the time limit
+            ft = ft < 0 ? 0 : ft;
+            const int first = fg < ft ? fg : ft;
+            env_fin = first < nsl;
+            ne = env_fin ? first + 1 : nsl;
+        }
+        // ---- stores of the executed slices
+        nc = W.cnt[rowlane ? s : 0];
+        if (in_chunk) {
+            const unsigned fe = (unsigned)(t0 + s) * (unsigned)E + (unsigned)e;
+            const unsigned recmask = (unsigned)W.cnt[31];
+            if (s < ne) {
+                ui = uact[lane];
+                if (recmask & 1u) reinterpret_cast<V2 *>(ra.pos_tr)[at] = W.pos[lane];
+                if (recmask & 2u) reinterpret_cast<V2 *>(ra.vel_tr)[at] = ui;        // :238
+                if (recmask & 4u) reinterpret_cast<Real *>(ra.r_tr)[at] = r_i;
+                if (recmask & 8u) reinterpret_cast<Real *>(ra.tr_tr)[at] = tr_i;
+                if (recmask & 16u) {
+                    V2 *zr = reinterpret_cast<V2 *>(ra.z_tr) + (size_t)at * (K + 1);
+                    int *nl = ra.Ni_tr + (size_t)at * (K + 1);
+#pragma unroll
+                    for (int kth = 0; kth <= K; ++kth) { zr[kth] = zrow[kth]; nl[kth] = nirow[kth]; }
+                }
+                {
+                    V2 acc = W.acc[lane];
+                    acc.x = add_rn(acc.x, r_i); acc.y = add_rn(acc.y, tr_i);
+                    W.acc[lane] = acc;
+                }
+                if (i == 0) {
+                    W.sumc[lane] += nc;
+                    if (recmask & 32u) ra.ncoll_tr[fe] = nc;
+                    if (recmask & 64u) ra.fin_tr[fe] = (env_fin && s == ne - 1) ? 1 : 0;
+                }
+            } else if (i == 0 && (recmask & 64u)) {
+                ra.fin_tr[fe] = 2;
+            }
+        }
+        __syncwarp();                                            // every lane has read its frame's count
+        if (rowlane && i == 0) W.cnt[s] = 0;
+        steps = t0 - ta + ne;
+        // ---- lane-load form: stage the next chunk's actions, fetch the one after
+        if (!act_mode && c + 1 < c1) {
+            int st1 = st + 1; st1 = st1 >= kRo2Stages ? 0 : st1;
+            if (rowlane) W.act[st1][lane] = upre;
+            upre = load_lane(c + 2);
+        }
+        if (++st == kRo2Stages) { st = 0; par ^= 1u; }
+        __syncwarp();
+        if (env_fin) {
+            if (ra.fin_tr) {                                     // the steps after the episode's end are not executed
+#pragma unroll 1
+                for (int t = t0 + TCW + lane; t < Tend; t += 32) ra.fin_tr[(size_t)t * E + e] = 2;
+            }
+            break;
+        }
+    }
+    if (dead && ra.fin_tr) {                                     // a segment behind the episode's end (or a done environment)
+#pragma unroll 1
+        for (int t = ta + lane; t < Tend; t += 32) ra.fin_tr[(size_t)t * E + e] = 2;
+    }
+    // ---- last executed step of the call: the step()-style outputs and the state in the live buffers
+    // (the segment in which the episode ended, or the last segment of the call)
+    if (!dead && (env_fin || Tend == T) && rowlane && s == ne - 1) {
+        reinterpret_cast<Real *>(a.r)[g] = r_i;
+        reinterpret_cast<Real *>(a.tr)[g] = tr_i;
+        V2 *zr = reinterpret_cast<V2 *>(a.z) + (size_t)g * (K + 1);
+        int *nl = a.Ni + (size_t)g * (K + 1);
+#pragma unroll
+        for (int kth = 0; kth <= K; ++kth) { zr[kth] = zrow[kth]; nl[kth] = nirow[kth]; }
+        reinterpret_cast<V2 *>(a.pos)[g] = W.pos[lane];
+        reinterpret_cast<V2 *>(a.vel)[g] = ui;
+        if (i == 0) { a.ncoll[e] = nc; a.fin[e] = env_fin ? 1 : 0; }
+    }
+    // ---- episode sums (train_problem.py:98-100): sum over the call of mean_i r, mean_i true_r, the
+    // collision counts and the steps; rows of a segment reduced over the warp, segments in time order
+    double sr = (double)W.acc[lane].x, stt = (double)W.acc[lane].y, sc = (double)W.sumc[lane];
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, w);
+        stt += __shfl_xor_sync(0xffffffffu, stt, w);
+        sc += __shfl_xor_sync(0xffffffffu, sc, w);
+    }
+    if (lane == 0) {
+        C.part[warp][0] = sr; C.part[warp][1] = stt; C.part[warp][2] = sc; C.part[warp][3] = (double)steps;
+        C.seg_fin[warp] = env_fin ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && alive0 && T > 0) {
+        double tr_ = 0, tt_ = 0, tc_ = 0, ts_ = 0;
+        int fin_any = 0;
+        for (int k = 0; k < S; ++k) {
+            tr_ += C.part[k][0]; tt_ += C.part[k][1]; tc_ += C.part[k][2]; ts_ += C.part[k][3];
+            fin_any |= C.seg_fin[k];
+        }
+        a.t[e] = tenv0 + (int)ts_;
+        if (ts_ > 0) {
+            if (fin_any) ra.done[e] = 1;
+            double *ag4 = ra.agg + (size_t)e * 4;
+            ag4[0] += tr_ / N; ag4[1] += tt_ / N; ag4[2] += tc_; ag4[3] += ts_;
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ds
