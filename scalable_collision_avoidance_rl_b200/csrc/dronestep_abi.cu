@@ -117,8 +117,12 @@ void plan_rollout2(ds_handle *h, const Real *dsv, const Real *dl, const Real *rd
     }
     a.delta_eff = clipcnt[0] != 0 ? (double)INFINITY : (double)dl[0];
     // one CTA per environment; its warps are the time segments of a call
-    int segs = env_int("DS_RO2_SEGS", ds::kRo2Threads / 32);
-    segs = segs < 1 ? 1 : (segs > ds::kRo2Threads / 32 ? ds::kRo2Threads / 32 : segs);
+    // enough warps to cover the SMs' resident slots (~24 per SM) about four times: short CTA lifetimes
+    // keep the drain at the end of the launch small; more segments only add prefix work
+    int segs = 1;
+    while (segs < ds::kRo2MaxSeg && (long long)h->E * segs < 4LL * 24 * h->sm_count) segs *= 2;
+    segs = env_int("DS_RO2_SEGS", segs);
+    segs = segs < 1 ? 1 : (segs > ds::kRo2MaxSeg ? ds::kRo2MaxSeg : segs);
     h->ro2_threads = 32 * segs;
     h->ro2_blocks = h->E;
     h->ro2_smem = cbytes + (size_t)segs * wbytes;
@@ -398,7 +402,7 @@ int launch_rollout2_n(ds_handle *h, const ds::Ro2Args &a, const CUtensorMap &tm,
     if (h->ro2_smem > 48 * 1024)
         DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ro2_smem));
     // the per-warp blocks need ~24 KB per CTA: leave the rest of the 256 KB to L1 (log table, spills)
-    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, env_int("DS_RO2_CARVE", 75)));
+    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, env_int("DS_RO2_CARVE", 100)));
     if (env_int("DS_PLAN_DEBUG", 0)) {
         int nb = -1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, h->ro2_threads, h->ro2_smem);

@@ -51,11 +51,11 @@ struct Ro2Args {
     int act_mode;           // action staging: 0 lane loads, 1 cp.async.bulk per slice, 2 one 2-D TMA tile per chunk
 };
 
-constexpr int kRo2Stages = 3;       // action ring depth (chunks)
-constexpr int kRo2Threads = 128;    // 4 warps = 4 time segments of one environment per CTA
+constexpr int kRo2Stages = 2;       // action ring depth (chunks): chunk c + 1 is in flight during chunk c
+constexpr int kRo2Threads = 256;    // up to 8 warps = 8 time segments of one environment per CTA
 constexpr int kRo2MaxSeg = 8;
 #ifndef DS_RO2_MINCTAS
-#define DS_RO2_MINCTAS 6            // 24 warps per SM: 80 registers per thread (72 spills 50 B, 64 spills 130 B)
+#define DS_RO2_MINCTAS 3            // 24 warps per SM: 80 registers per thread
 #endif
 
 __host__ __device__ inline size_t ro2_align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -64,18 +64,22 @@ __host__ __device__ inline size_t ro2_align16(size_t b) { return (b + 15) & ~(si
 template <typename Real, int N> struct alignas(128) Ro2Warp {
     using V2 = typename vec2_of<Real>::type;
     static constexpr int TCW = 32 / N, RW = TCW * N, HP = (N + 1) / 2;
-    static constexpr int LW = (RW * (N - 1) < 128) ? RW * (N - 1) : 128;          // ordered result slots
-    static constexpr int LU = (RW * (N - 1) / 2 < 64) ? RW * (N - 1) / 2 : 64;    // unordered list entries
-    static constexpr int GR = LW / (N - 1);                                       // rows per group, dense mode
+    // TABLE: results in a dense [row][partner] table and a list with room for every pair of the
+    // chunk (small N); otherwise row-contiguous segments and a list of bounded capacity, with the
+    // exact group-wise evaluation for frames that overflow it
+    static constexpr bool TABLE = (size_t)RW * N * sizeof(V2) <= 5120;
+    static constexpr int LW = TABLE ? RW * N : ((RW * (N - 1) < 128) ? RW * (N - 1) : 128);         // result slots
+    static constexpr int LU = TABLE ? RW * (N - 1) / 2 : ((RW * (N - 1) / 2 < 64) ? RW * (N - 1) / 2 : 64);   // list entries
+    static constexpr int GR = LW / (N - 1);                                       // rows per group (overflowing frames)
     static constexpr int ASTR = (int)(((RW * sizeof(V2) + 127) / 128) * 128 / sizeof(V2));   // stage stride: 128-byte aligned (TMA)
     V2 act[kRo2Stages][ASTR]; // action ring: [slice][agent] of a chunk, as in global memory
     V2 pos[32];               // positions of the chunk's rows (row = lane)
-    V2 pend[32];              // agent's position after the previous chunk (lane (s, i): agent i; same in every s)
+    V2 pend[N];               // agent's position after the previous chunk
     V2 acc[32];               // running episode sums (r, true_r) of the lane's rows
     int sumc[32];             // running collision count of the slice's frames (lanes with i == 0)
     V2 res[LW];               // (d, log term) per ordered near pair, row-contiguous, ascending j
     float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
-    uint2 rowinfo[32];        // (near mask, first result slot) of each row
+    uint2 rowinfo[TABLE ? 1 : 32];   // (near mask, first result slot) of each row (segment layout only)
     unsigned ent[LU];         // unordered near pairs
     unsigned umask[32];       // near AND not clipped (pair lanes clear the rare clipped-near bits)
     int cnt[32];              // collision count per frame (slice)
@@ -201,6 +205,35 @@ __device__ __forceinline__ void ro2_fold(const typename vec2_of<Real>::type *__r
     }
 }
 
+// The same fold over a row of the dense [row][partner] table: partner j's result at rp[j].
+template <typename Real, int K>
+__device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp, unsigned mm, Real ds,
+                                               Real delta_eff, Real &sum_all, Real &sum_loc, Real (&nd)[K], int (&nj)[K])
+{
+    using V2 = typename vec2_of<Real>::type;
+    const int iters = __reduce_max_sync(0xffffffffu, __popc(mm));
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const bool on = mm != 0;
+        const int j = __ffs((int)mm) - 1;
+        mm &= mm - 1;
+        V2 dv; dv.x = ds; dv.y = 0;
+        if (on) dv = rp[j];
+        sum_all = add_rn(sum_all, dv.y);                                                       // :283
+        sum_loc = add_rn(sum_loc, mul_rn(dv.y, (dv.x <= delta_eff) ? (Real)1 : (Real)0));      // :282
+        bool lt[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) lt[q] = dv.x < nd[q];
+#pragma unroll
+        for (int q = K - 1; q > 0; --q) {
+            nd[q] = lt[q - 1] ? nd[q - 1] : (lt[q] ? dv.x : nd[q]);
+            nj[q] = lt[q - 1] ? nj[q - 1] : (lt[q] ? j : nj[q]);
+        }
+        nd[0] = lt[0] ? dv.x : nd[0];
+        nj[0] = lt[0] ? j : nj[0];
+    }
+}
+
 // -np.nan_to_num(v) (drone_env.py:287-288); the rewards are finite unless a position is not
 DS_HD double ro2_neg_nan_to_num(double v)
 {
@@ -307,32 +340,45 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     if (alive0 && c0 > 0 && c0 < nchunks && tlim >= ta) {
         V2 pm{};
         const V2 xF = C.cF[i];
-        for (int cb = 0; cb < c0 && tstar == 0x7fffffff; cb += 8) {
+        // every slice of a chunk in front of the segment lies inside the call: no bounds to test
+        const V2 *ap = reinterpret_cast<const V2 *>(ra.actions) + ((size_t)s * EN + g);
+        const uint8_t *xp = ra.aidx + ((size_t)s * EN + g);
+        const size_t cstep = (size_t)TCW * EN;
+        auto fetch = [&]() -> V2 {
+            V2 u{};
+            if (rowlane) u = direct ? *ap : atab[*xp];
+            ap += cstep; xp += cstep;
+            return u;
+        };
+        auto prefix_chunk = [&](const V2 &u, int c, int par2) -> bool {
+            V2 *buf = &W.act[par2][0];
+            if (rowlane) buf[lane] = u;
+            __syncwarp();
+            integrate(buf + i, pend, pm);
+            // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
+            const Real gx = sub_rn(xF.x, pm.x), gy = sub_rn(xF.y, pm.y);
+            const bool atg = rowlane && add_rn(mul_rn(gx, gx), mul_rn(gy, gy)) <= (Real)A.goal_t2;
+            const unsigned gbal = __ballot_sync(0xffffffffu, atg);
+            const bool slice_goal = rowlane && i == 0 && (((gbal >> (lane & 31)) & fullN) == fullN);
+            const unsigned sbal = __ballot_sync(0xffffffffu, slice_goal);
+            if (sbal) tstar = c * TCW + (__ffs((int)sbal) - 1) / N;
+            return sbal != 0;
+        };
+        int c = 0;
+        bool hit = false;
+        for (; c + 8 <= c0 && !hit; c += 8) {                    // eight chunks in flight
             V2 u8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) u8[q] = load_lane(cb + q);
+            for (int q = 0; q < 8; ++q) u8[q] = fetch();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = cb + q;
-                if (c < c0) {                                    // warp-uniform
-                    V2 *buf = &W.act[q & 1][0];
-                    if (rowlane) buf[lane] = u8[q];
-                    __syncwarp();
-                    integrate(buf + i, pend, pm);
-                    // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
-                    const Real gx = sub_rn(xF.x, pm.x), gy = sub_rn(xF.y, pm.y);
-                    const bool atg = rowlane && add_rn(mul_rn(gx, gx), mul_rn(gy, gy)) <= (Real)A.goal_t2;
-                    const unsigned gbal = __ballot_sync(0xffffffffu, atg);
-                    const bool slice_goal = rowlane && i == 0 && (((gbal >> (lane & 31)) & fullN) == fullN);
-                    const unsigned sbal = __ballot_sync(0xffffffffu, slice_goal);
-                    if (sbal && tstar == 0x7fffffff) tstar = c * TCW + (__ffs((int)sbal) - 1) / N;
-                }
-            }
+            for (int q = 0; q < 8; ++q)
+                if (!hit) hit = prefix_chunk(u8[q], c + q, q & 1);
         }
+        for (; c < c0 && !hit; ++c) hit = prefix_chunk(fetch(), c, c & 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring is next written by TMA copies
         __syncwarp();
     }
-        W.pend[lane] = pend;
+        if (lane < N) W.pend[lane] = pend;
         V2 z2; z2.x = 0; z2.y = 0;
         W.acc[lane] = z2;
         W.sumc[lane] = 0;
@@ -366,10 +412,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     V2 upre{};
     if (!dead) {
         if (act_mode) {
-            if (lane == 0) {
-                issue_tma(c0, 0);
-                if (c0 + 1 < c1) issue_tma(c0 + 1, 1);
-            }
+            if (lane == 0) issue_tma(c0, 0);
         } else {
             if (rowlane) W.act[0][lane] = load_lane(c0);
             upre = load_lane(c0 + 1);
@@ -391,19 +434,17 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     for (int c = dead ? c1 : c0; c < c1; ++c, t0 += TCW, at += (unsigned)TCW * EN) {
         const bool in_chunk = rowlane && (t0 + s < T);
         const V2 *uact = &W.act[st][0];
-        // ---- next-but-one chunk's actions on their way; this chunk's have landed
+        // ---- the next chunk's actions on their way; this chunk's have landed
         if (act_mode) {
-            if (lane == 0 && c + 2 < c1) {
-                int st2 = st + 2; st2 = st2 >= kRo2Stages ? st2 - kRo2Stages : st2;
-                issue_tma(c + 2, st2);                           // the stage last read in chunk c - 1
-            }
+            if (lane == 0 && c + 1 < c1) issue_tma(c + 1, st ^ 1);   // the stage last read in chunk c - 1
             ro2_mbar_wait(&W.mbar[st], par);
         }
         float fx, fy;
         {
-            V2 pend = W.pend[lane], pm{};
+            V2 pend = W.pend[i], pm{};
             integrate(uact + i, pend, pm);
-            W.pend[lane] = pend;
+            __syncwarp();                                        // every lane has read the old position
+            if (lane < N) W.pend[lane] = pend;
             // f32 copy for pass 1: component (i & 1) of x / y in float4 (i >> 1) of frame s
             const bool okf = fabs(pm.x) < (Real)1024 && fabs(pm.y) < (Real)1024;   // false for NaN / inf too
             fx = okf ? (float)pm.x : __int_as_float(0x7fc00000);
@@ -421,6 +462,65 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         unsigned m = ro2_pass1<N>(&W.posf[(rowlane ? s : 0) * HP], -fx, -fy, A.thr2f) & ~(1u << i);
         m = in_chunk ? m : 0u;
         const unsigned mU = m & (0xfffffffeu << i);              // partners above i
+        Real sum_all = 0, sum_loc = 0, nd[K];
+        int nj[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) { nd[q] = ds; nj[q] = -1; }
+        if constexpr (WS::TABLE) {
+            // ---- list of the UNORDERED near pairs (j > i); offsets from bit-sliced ballots (no
+            // dependent shuffle chain): count < 2^NB
+            constexpr int NB = (N <= 2) ? 1 : (N <= 4) ? 2 : (N <= 8) ? 3 : (N <= 16) ? 4 : 5;
+            const int cUl = __popc(mU);
+            const unsigned ltmask = (1u << lane) - 1u;
+            int baseU = 0, totU = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (cUl >> b) & 1);
+                baseU += __popc(bal & ltmask) << b;
+                totU += __popc(bal) << b;
+            }
+            {
+                W.umask[lane] = m;
+                unsigned *ep = W.ent + baseU;
+                unsigned mm = mU;
+                const unsigned ew = (unsigned)lane | ((unsigned)i << 5);
+                const int iters = __reduce_max_sync(0xffffffffu, cUl);
+#pragma unroll 1
+                for (int it = 0; it < iters; ++it) {
+                    if (mm) {
+                        const int j = __ffs((int)mm) - 1;
+                        mm &= mm - 1;
+                        *ep++ = ew | ((unsigned)j << 10);
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- pass 2: one unordered near pair per lane per round; result to both rows of the table
+#pragma unroll 1
+            for (int q0 = 0; q0 < totU; q0 += 32) {
+                const int q = q0 + lane;
+                const bool valid = q < totU;
+                const unsigned w = W.ent[valid ? q : 0];
+                const int ri = (int)(w & 31u), ii = (int)((w >> 5) & 31u), j = (int)(w >> 10);
+                const int rj = ri - ii + j;
+                const V2 pi = W.pos[ri], pj = W.pos[rj];
+                V2 dv;
+                bool coll;
+                ro2_eval_pair<Real>(dv.x, dv.y, coll, pi.x, pi.y, pj.x, pj.y, ds, rad, (Real)A.log_ds, (Real)A.inv_ds,
+                                    a.log_mode, (Real)a.zero_eps, (Real)a.sentinel, logtab);
+                if (valid) {
+                    W.res[ri * N + j] = dv;
+                    W.res[rj * N + ii] = dv;
+                    if (coll) atomicAdd(&W.cnt[(ri - ii) / N], 2);                // both ordered pairs collide (:284,327)
+                    if (!(dv.x != ds)) {                                          // near but clipped (inside the f32 margin)
+                        atomicAnd(&W.umask[ri], ~(1u << j));
+                        atomicAnd(&W.umask[rj], ~(1u << ii));
+                    }
+                }
+            }
+            __syncwarp();
+            ro2_fold_table<Real, K>(W.res + lane * N, m, ds, delta_eff, sum_all, sum_loc, nd, nj);
+        } else {
         const int cFl = __popc(m), cUl = __popc(mU);
         int incl = cUl | (cFl << 16);                            // both counts in one scan
 #pragma unroll
@@ -431,10 +531,6 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         const int tot = __shfl_sync(0xffffffffu, incl, 31);
         const int totU = tot & 0xffff, totF = tot >> 16;
         const int baseF = (incl >> 16) - cFl;
-        Real sum_all = 0, sum_loc = 0, nd[K];
-        int nj[K];
-#pragma unroll
-        for (int q = 0; q < K; ++q) { nd[q] = ds; nj[q] = -1; }
         if (totU <= WS::LU && totF <= WS::LW) {                  // warp-uniform
             // ---- list of the UNORDERED near pairs (j > i)
             {
@@ -516,6 +612,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                                   sum_all, sum_loc, nd, nj);
                 __syncwarp();
             }
+        }
         }
         // ---- the row: k nearest, goal cost, rewards, observation (all lanes; stores predicated)
         {
@@ -623,11 +720,11 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         steps = t0 - ta + ne;
         // ---- lane-load form: stage the next chunk's actions, fetch the one after
         if (!act_mode && c + 1 < c1) {
-            int st1 = st + 1; st1 = st1 >= kRo2Stages ? 0 : st1;
-            if (rowlane) W.act[st1][lane] = upre;
+            if (rowlane) W.act[st ^ 1][lane] = upre;
             upre = load_lane(c + 2);
         }
-        if (++st == kRo2Stages) { st = 0; par ^= 1u; }
+        st ^= 1;
+        if (st == 0) par ^= 1u;
         __syncwarp();
         if (env_fin) {
             if (ra.fin_tr) {                                     // the steps after the episode's end are not executed

@@ -9,7 +9,9 @@ minpct = float(sys.argv[4]) if len(sys.argv) > 4 else 0.15
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw))); hdr = rows[1]; col = {h: i for i, h in enumerate(hdr)}; sass = rows[2:]
-so = os.path.join(ROOT, "scalable_collision_avoidance_rl_b200", "libdronestep.so")
+so = os.path.join(os.path.dirname(os.path.abspath(rep)), "lib.so")      # the library the report was taken with (tools/dev_cycle.sh)
+if not os.path.exists(so):
+    so = os.path.join(ROOT, "scalable_collision_avoidance_rl_b200", "libdronestep.so")
 with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, capture_output=True)
     cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
