@@ -419,6 +419,23 @@ int launch_rollout2(ds_handle *h, const ds::RolloutArgs &ra, cudaStream_t st)
     ds::Ro2Args a = h->ro2;
     a.ra = ra;
     a.goal_t2 = h->real_bytes == 8 ? goal_threshold_sq<double>(ra.s.goal_tol) : goal_threshold_sq<float>(ra.s.goal_tol);
+    {   // time segments: segment k pays rho chunk-equivalents per chunk in front of it (its prefix pass), so
+        // its own length shrinks accordingly: L_k = L_0 - rho * (L_0 + ... + L_{k-1})
+        const int S = h->ro2_threads / 32, TCw = 32 / h->n;
+        const int nchunks = (ra.T + TCw - 1) / TCw;
+        const double rho = env_int("DS_RO2_RHO_PERMILLE", 70) / 1000.0;
+        double w[ds::kRo2MaxSeg], acc = 0, tot = 0;
+        for (int k = 0; k < S; ++k) { w[k] = 1.0 - rho * acc; w[k] = w[k] < 0.1 ? 0.1 : w[k]; acc += w[k]; tot += w[k]; }
+        double run = 0;
+        a.seg_c0[0] = 0;
+        for (int k = 0; k < S; ++k) {
+            run += w[k];
+            int c = (int)std::lround(nchunks * run / tot);
+            c = c < a.seg_c0[k] ? a.seg_c0[k] : (c > nchunks ? nchunks : c);
+            a.seg_c0[k + 1] = (k == S - 1) ? nchunks : c;
+        }
+        for (int k = S + 1; k <= ds::kRo2MaxSeg; ++k) a.seg_c0[k] = nchunks;
+    }
     if (a.goal_t2 < 0 && !(ra.s.goal_tol >= 0)) a.goal_t2 = -1.0;
     // TMA: 16-byte aligned source, slice blocks a multiple of 16 bytes.  2: one 2-D tile per chunk
     // (tensor map over [T][E * n * 2] Reals); 1: one 1-D bulk copy per slice; 0: per-lane loads.

@@ -49,6 +49,8 @@ struct Ro2Args {
     double goal_t2;         // largest x with sqrt_rn(x) <= goal_tol: the goal test without the square root
     float thr2f;            // pass-1 threshold of the packed-f32 filter (squared, with margin)
     int act_mode;           // action staging: 0 lane loads, 1 cp.async.bulk per slice, 2 one 2-D TMA tile per chunk
+    int seg_c0[9];          // first chunk of every time segment (seg_c0[S] = number of chunks): later segments are
+                            // shorter, by the cost of the prefix pass in front of them, so that a CTA's warps finish together
 };
 
 constexpr int kRo2Stages = 2;       // action ring depth (chunks): chunk c + 1 is in flight during chunk c
@@ -205,32 +207,45 @@ __device__ __forceinline__ void ro2_fold(const typename vec2_of<Real>::type *__r
     }
 }
 
-// The same fold over a row of the dense [row][partner] table: partner j's result at rp[j].
+// The same fold over a row of the dense [row][partner] table: partner j's result at rp[j].  Two
+// partners per iteration (both loads in flight together).
+template <typename Real, int K>
+__device__ __forceinline__ void ro2_fold_step(Real dx, Real dy, int j, Real delta_eff, Real &sum_all, Real &sum_loc,
+                                              Real (&nd)[K], int (&nj)[K])
+{
+    sum_all = add_rn(sum_all, dy);                                                         // :283
+    sum_loc = add_rn(sum_loc, mul_rn(dy, (dx <= delta_eff) ? (Real)1 : (Real)0));          // :282
+    bool lt[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) lt[q] = dx < nd[q];                 // false for NaN; clipped (== d_safety) never enters
+#pragma unroll
+    for (int q = K - 1; q > 0; --q) {
+        nd[q] = lt[q - 1] ? nd[q - 1] : (lt[q] ? dx : nd[q]);
+        nj[q] = lt[q - 1] ? nj[q - 1] : (lt[q] ? j : nj[q]);
+    }
+    nd[0] = lt[0] ? dx : nd[0];
+    nj[0] = lt[0] ? j : nj[0];
+}
 template <typename Real, int K>
 __device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp, unsigned mm, Real ds,
                                                Real delta_eff, Real &sum_all, Real &sum_loc, Real (&nd)[K], int (&nj)[K])
 {
     using V2 = typename vec2_of<Real>::type;
-    const int iters = __reduce_max_sync(0xffffffffu, __popc(mm));
+    const int iters = (__reduce_max_sync(0xffffffffu, __popc(mm)) + 1) >> 1;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const bool on = mm != 0;
-        const int j = __ffs((int)mm) - 1;
+        const bool on0 = mm != 0;
+        const int j0 = __ffs((int)mm) - 1;
         mm &= mm - 1;
-        V2 dv; dv.x = ds; dv.y = 0;
-        if (on) dv = rp[j];
-        sum_all = add_rn(sum_all, dv.y);                                                       // :283
-        sum_loc = add_rn(sum_loc, mul_rn(dv.y, (dv.x <= delta_eff) ? (Real)1 : (Real)0));      // :282
-        bool lt[K];
-#pragma unroll
-        for (int q = 0; q < K; ++q) lt[q] = dv.x < nd[q];
-#pragma unroll
-        for (int q = K - 1; q > 0; --q) {
-            nd[q] = lt[q - 1] ? nd[q - 1] : (lt[q] ? dv.x : nd[q]);
-            nj[q] = lt[q - 1] ? nj[q - 1] : (lt[q] ? j : nj[q]);
-        }
-        nd[0] = lt[0] ? dv.x : nd[0];
-        nj[0] = lt[0] ? j : nj[0];
+        const bool on1 = mm != 0;
+        const int j1 = __ffs((int)mm) - 1;
+        mm &= mm - 1;
+        V2 d0, d1;
+        d0.x = ds; d0.y = 0; d1.x = ds; d1.y = 0;
+        if (on0) d0 = rp[j0];
+        if (on1) d1 = rp[j1];
+        ro2_fold_step<Real, K>(d0.x, d0.y, j0, delta_eff, sum_all, sum_loc, nd, nj);
+        ro2_fold_step<Real, K>(d1.x, d1.y, j1, delta_eff, sum_all, sum_loc, nd, nj);
     }
 }
 
@@ -300,8 +315,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
 
     // ---- the call's time axis is cut into S segments of whole chunks; warp k owns segment k
     const int nchunks = (T + TCW - 1) / TCW;
-    const int Cs = (nchunks + S - 1) / S;                        // chunks per segment
-    const int c0 = warp * Cs, c1 = (c0 + Cs < nchunks) ? c0 + Cs : nchunks;
+    const int c0 = A.seg_c0[warp], c1 = A.seg_c0[warp + 1];      // this segment's chunks
     const int ta = c0 * TCW, Tend = (c1 * TCW < T) ? c1 * TCW : T;   // steps [ta, Tend) of the call
     const bool alive0 = ra.done[e] == 0;
     const int tenv0 = a.t[e];
@@ -486,12 +500,12 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 const unsigned ew = (unsigned)lane | ((unsigned)i << 5);
                 const int iters = __reduce_max_sync(0xffffffffu, cUl);
 #pragma unroll 1
-                for (int it = 0; it < iters; ++it) {
-                    if (mm) {
-                        const int j = __ffs((int)mm) - 1;
-                        mm &= mm - 1;
-                        *ep++ = ew | ((unsigned)j << 10);
-                    }
+                for (int it = 0; it < iters; ++it) {             // straight-line body: lanes out of pairs store nothing
+                    const bool on = mm != 0;
+                    const unsigned j = (unsigned)(__ffs((int)mm) - 1);
+                    if (on) *ep = ew | (j << 10);
+                    ep += on ? 1 : 0;
+                    mm &= mm - 1;
                 }
             }
             __syncwarp();
