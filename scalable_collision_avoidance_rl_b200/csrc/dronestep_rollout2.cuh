@@ -226,24 +226,21 @@ __device__ __forceinline__ void ro2_fold_step(Real dx, Real dy, int j, Real delt
     nd[0] = lt[0] ? dx : nd[0];
     nj[0] = lt[0] ? j : nj[0];
 }
+// rp[i] (the row's own slot) holds (d_safety, +0) for the whole call: never a candidate, adds nothing --
+// what a lane that has run out of partners folds.
 template <typename Real, int K>
-__device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp, unsigned mm, Real ds,
+__device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp, unsigned mm, int i,
                                                Real delta_eff, Real &sum_all, Real &sum_loc, Real (&nd)[K], int (&nj)[K])
 {
     using V2 = typename vec2_of<Real>::type;
     const int iters = (__reduce_max_sync(0xffffffffu, __popc(mm)) + 1) >> 1;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const bool on0 = mm != 0;
-        const int j0 = __ffs((int)mm) - 1;
+        const int j0 = mm ? __ffs((int)mm) - 1 : i;
         mm &= mm - 1;
-        const bool on1 = mm != 0;
-        const int j1 = __ffs((int)mm) - 1;
+        const int j1 = mm ? __ffs((int)mm) - 1 : i;
         mm &= mm - 1;
-        V2 d0, d1;
-        d0.x = ds; d0.y = 0; d1.x = ds; d1.y = 0;
-        if (on0) d0 = rp[j0];
-        if (on1) d1 = rp[j1];
+        const V2 d0 = rp[j0], d1 = rp[j1];
         ro2_fold_step<Real, K>(d0.x, d0.y, j0, delta_eff, sum_all, sum_loc, nd, nj);
         ro2_fold_step<Real, K>(d1.x, d1.y, j1, delta_eff, sum_all, sum_loc, nd, nj);
     }
@@ -332,17 +329,21 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         return u;
     };
     // one chunk of sequential, bit-exact single-integrator steps of agent i (A = I, B = dt I,
-    // drone_env.py:78-79,235) from the staged actions ua[q * N]; lane (s, i) keeps slice s
+    // drone_env.py:78-79,235) from the staged actions ua[q * N]: lane (s, i) takes the steps up to its
+    // own slice, p: position after the previous chunk -> position at slice s.  The lanes of the
+    // chunk's last slice end with the position the next chunk starts from.
     const Real dt = (Real)a.dt;
-    auto integrate = [&](const V2 *ua, V2 &pend, V2 &pm) {
+    auto integrate = [&](const V2 *ua, V2 &p) {
 #pragma unroll
         for (int q = 0; q < TCW; ++q) {
             const V2 u = ua[q * N];
-            pend.x = add_rn(pend.x, mul_rn(dt, u.x));
-            pend.y = add_rn(pend.y, mul_rn(dt, u.y));
-            if (q == s) pm = pend;
+            if (q <= s) {
+                p.x = add_rn(p.x, mul_rn(dt, u.x));
+                p.y = add_rn(p.y, mul_rn(dt, u.y));
+            }
         }
     };
+    const int last_lane = (TCW - 1) * N + i;                     // the lane of agent i in the chunk's last slice
 
     // ---- prefix: the state at the start of this warp's segment.  Only the integrator runs over the
     // steps in front of it (two dependent fp64 operations per step; actions fetched eight chunks
@@ -354,21 +355,14 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     if (alive0 && c0 > 0 && c0 < nchunks && tlim >= ta) {
         V2 pm{};
         const V2 xF = C.cF[i];
-        // every slice of a chunk in front of the segment lies inside the call: no bounds to test
-        const V2 *ap = reinterpret_cast<const V2 *>(ra.actions) + ((size_t)s * EN + g);
-        const uint8_t *xp = ra.aidx + ((size_t)s * EN + g);
-        const size_t cstep = (size_t)TCW * EN;
-        auto fetch = [&]() -> V2 {
-            V2 u{};
-            if (rowlane) u = direct ? *ap : atab[*xp];
-            ap += cstep; xp += cstep;
-            return u;
-        };
         auto prefix_chunk = [&](const V2 &u, int c, int par2) -> bool {
             V2 *buf = &W.act[par2][0];
             if (rowlane) buf[lane] = u;
             __syncwarp();
-            integrate(buf + i, pend, pm);
+            pm = pend;
+            integrate(buf + i, pm);
+            pend.x = __shfl_sync(0xffffffffu, pm.x, last_lane);
+            pend.y = __shfl_sync(0xffffffffu, pm.y, last_lane);
             // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
             const Real gx = sub_rn(xF.x, pm.x), gy = sub_rn(xF.y, pm.y);
             const bool atg = rowlane && add_rn(mul_rn(gx, gx), mul_rn(gy, gy)) <= (Real)A.goal_t2;
@@ -378,17 +372,28 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             if (sbal) tstar = c * TCW + (__ffs((int)sbal) - 1) / N;
             return sbal != 0;
         };
-        int c = 0;
-        bool hit = false;
-        for (; c + 8 <= c0 && !hit; c += 8) {                    // eight chunks in flight
-            V2 u8[8];
+        // every slice of a chunk in front of the segment lies inside the call: no bounds to test
+        auto run_prefix = [&](auto fetch) {
+            int c = 0;
+            bool hit = false;
+            for (; c + 8 <= c0 && !hit; c += 8) {                // eight chunks in flight
+                V2 u8[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) u8[q] = fetch();
+                for (int q = 0; q < 8; ++q) u8[q] = fetch();
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (!hit) hit = prefix_chunk(u8[q], c + q, q & 1);
+                for (int q = 0; q < 8; ++q)
+                    if (!hit) hit = prefix_chunk(u8[q], c + q, q & 1);
+            }
+            for (; c < c0 && !hit; ++c) hit = prefix_chunk(fetch(), c, c & 1);
+        };
+        const size_t cstep = (size_t)TCW * EN;
+        if (direct) {
+            const V2 *ap = reinterpret_cast<const V2 *>(ra.actions) + ((size_t)s * EN + g);
+            run_prefix([&]() -> V2 { V2 u{}; if (rowlane) u = *ap; ap += cstep; return u; });
+        } else {
+            const uint8_t *xp = ra.aidx + ((size_t)s * EN + g);
+            run_prefix([&]() -> V2 { V2 u{}; if (rowlane) u = atab[*xp]; xp += cstep; return u; });
         }
-        for (; c < c0 && !hit; ++c) hit = prefix_chunk(fetch(), c, c & 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring is next written by TMA copies
         __syncwarp();
     }
@@ -396,6 +401,10 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         V2 z2; z2.x = 0; z2.y = 0;
         W.acc[lane] = z2;
         W.sumc[lane] = 0;
+        if constexpr (WS::TABLE) {                              // the rows' own slots of the result table: the fold's neutral element
+            V2 nv; nv.x = (Real)A.ds; nv.y = 0;
+            if (rowlane) W.res[lane * N + i] = nv;
+        }
     }
 
     // ---- this warp's segment
@@ -409,11 +418,15 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     // ---- action staging.  TMA: lane 0 brings chunk c's [TCW][N][2] block into ring stage (c - c0) % 3
     // (one 2-D tile, or one 1-D bulk copy per slice); lane-load form: every row lane holds the action
     // of its row one chunk ahead.
+    const unsigned act_s32 = ro2_smem_u32(&W.act[0][0]), mbar_s32 = ro2_smem_u32(&W.mbar[0]);
+    const unsigned long long tmap_addr = reinterpret_cast<unsigned long long>(&tmap);
     auto issue_tma = [&](int c, int st) {                        // lane 0 only
         constexpr unsigned blk = (unsigned)N * (unsigned)sizeof(V2);
         if (act_mode == 2) {
-            ro2_mbar_expect(&W.mbar[st], (unsigned)TCW * blk);
-            ro2_tma_g2s_2d(&W.act[st][0], &tmap, e * N * 2, c * TCW, &W.mbar[st]);
+            const unsigned bar = mbar_s32 + 8u * (unsigned)st, dst = act_s32 + (unsigned)(WS::ASTR * sizeof(V2)) * (unsigned)st;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)TCW * blk) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                             dst), "l"(tmap_addr), "r"(e * N * 2), "r"(c * TCW), "r"(bar) : "memory");
         } else {
             const int t0c = c * TCW;
             const int nslc = (T - t0c < TCW) ? (T - t0c) : TCW;
@@ -455,10 +468,10 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         }
         float fx, fy;
         {
-            V2 pend = W.pend[i], pm{};
-            integrate(uact + i, pend, pm);
+            V2 pm = W.pend[i];
+            integrate(uact + i, pm);
             __syncwarp();                                        // every lane has read the old position
-            if (lane < N) W.pend[lane] = pend;
+            if (rowlane && s == TCW - 1) W.pend[i] = pm;
             // f32 copy for pass 1: component (i & 1) of x / y in float4 (i >> 1) of frame s
             const bool okf = fabs(pm.x) < (Real)1024 && fabs(pm.y) < (Real)1024;   // false for NaN / inf too
             fx = okf ? (float)pm.x : __int_as_float(0x7fc00000);
@@ -533,7 +546,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 }
             }
             __syncwarp();
-            ro2_fold_table<Real, K>(W.res + lane * N, m, ds, delta_eff, sum_all, sum_loc, nd, nj);
+            ro2_fold_table<Real, K>(W.res + lane * N, m, i, delta_eff, sum_all, sum_loc, nd, nj);
         } else {
         const int cFl = __popc(m), cUl = __popc(mU);
         int incl = cUl | (cFl << 16);                            // both counts in one scan
