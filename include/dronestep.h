@@ -171,8 +171,12 @@ int ds_reduce_aggregates(ds_handle *h, const double *agg_dev, double *out_dev, v
  * reference's learners compute on the host from their ExperienceBuffers (SAC_agents.py:304-310 /
  * 108-113: G_i(t) = G_i(t+1) * discount + r_i(t) backwards from the episode's last step;
  * SAC_agents.py:333-345: A_i(t) = sum over j in N_i(t) of (G_j(t) - V_i(t)), in list order).
- * Inputs are the trajectory buffers ds_rollout writes (device pointers); an environment's episode
- * ends at its last executed step (finished code != 2); not-executed steps get zeros. */
+ * reward_tr / finished_tr are the trajectory buffers ds_rollout writes (device pointers); an
+ * environment's episode ends at its last executed step (finished code != 2); not-executed steps get
+ * zeros.  Ni_tr[t] must be the neighbour lists of the state step t was TAKEN FROM, N_i(s_t) -- the
+ * reference stores `Ni = env.Ni` before `env.step` (train_problem.py:84-96).  ds_rollout's Ni_tr[t]
+ * is the observation step t RETURNED, N_i(s_{t+1}): shift it by one step and put the pre-call
+ * observation (io->Ni before the rollout) in front (the Python mirror: pre_step_observations()). */
 typedef struct ds_returns_io {
     int32_t T;
     int32_t _pad;
@@ -294,11 +298,14 @@ int ds_step_host_block(ds_handle *h, const void *actions_host, const ds_params *
  * chunk c's kernel on two library-owned copy streams, with double-buffered
  * staging owned by the handle.  Trajectory pointers may each be NULL.  Runs from
  * the state in io with done = 0 and agg = 0; returns after one synchronise. */
+#define DS_HOST_COMPACT_OBS 1   /* ds_host_rollout.flags: z_tr is float32 [T][E][n][k+1][cols] (what the reference's
+                                   actors cast the observation to, utils.py:305) and Ni_tr is u8 [T][E][n][k+1]
+                                   (255 = none): 27 instead of 60 bytes per agent-step across PCIe (k = 2) */
 typedef struct ds_host_rollout {
     int32_t T;
     int32_t chunk;
     int32_t n_actions;
-    int32_t _pad;
+    int32_t flags;              /* 0 or DS_HOST_COMPACT_OBS */
     const void *actions;        /* host Real [T][E][n][2], or NULL for index mode */
     const uint8_t *action_idx;  /* host u8 [T][E][n] */
     const void *action_table;   /* host Real [n_actions][2] */
@@ -308,8 +315,8 @@ typedef struct ds_host_rollout {
                                    crosses PCIe; vel_tr == actions (alias) costs nothing */
     void *reward_tr;
     void *true_reward_tr;
-    void *z_tr;
-    int32_t *Ni_tr;
+    void *z_tr;                 /* Real, or float32 with DS_HOST_COMPACT_OBS */
+    int32_t *Ni_tr;             /* i32, or u8 (cast the pointer) with DS_HOST_COMPACT_OBS */
     int32_t *ncoll_tr;
     uint8_t *finished_tr;
     double *agg;                /* host f64 [E][4] out (may be NULL) */

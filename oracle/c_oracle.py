@@ -60,6 +60,7 @@ def lib():
         _lib = ctypes.CDLL(path)
         _lib.oracle_step_batch.restype = ctypes.c_int
         _lib.oracle_rollout_batch.restype = ctypes.c_int
+        _lib.oracle_rollout_batch_obs.restype = ctypes.c_int
         _lib.oracle_returns_batch.restype = ctypes.c_int
         _lib.oracle_control_batch.restype = ctypes.c_int
     return _lib
@@ -136,8 +137,9 @@ class OracleEnv:
         act = np.ascontiguousarray(np.asarray(actions, np.float64).reshape(self.E, self.n, 2))
         return self._call(act)
 
-    def rollout(self, act_stream, record=True):
-        """T steps from act_stream[T,E,n,2]; returns dict of aggregates/trajectories."""
+    def rollout(self, act_stream, record=True, record_obs=False):
+        """T steps from act_stream[T,E,n,2]; returns dict of aggregates/trajectories.  record_obs:
+        also the observation every executed step returned (z_tr, Ni_tr, tie_tr, pos_tr)."""
         act = np.ascontiguousarray(np.asarray(act_stream, np.float64))
         T = act.shape[0]
         assert act.shape == (T, self.E, self.n, 2)
@@ -148,17 +150,23 @@ class OracleEnv:
         t_tr = np.zeros((T, E, n)) if record else None
         c_tr = np.zeros((T, E), np.int32) if record else None
         f_tr = np.zeros((T, E), np.uint8) if record else None
-        rc = lib().oracle_rollout_batch(
+        k = self.k
+        z_tr = np.zeros((T, E, n, k + 1, self.cols)) if record_obs else None
+        Ni_tr = np.full((T, E, n, k + 1), -1, np.int32) if record_obs else None
+        tie_tr = np.zeros((T, E, n), np.uint8) if record_obs else None
+        pos_tr = np.zeros((T, E, n, 2)) if record_obs else None
+        rc = lib().oracle_rollout_batch_obs(
             E, n, self.k, int(self.simplify), T, ctypes.byref(self.params),
             _p(self.pos), _p(self.vel), _p(self.radius), _p(act), _p(self.xF),
             _p(self.d_safety), _p(self.deltas), _p(self.r), _p(self.true_r), _p(self.z),
             _p(self.Ni), _p(self.ncoll), _p(self.finished), _p(self.t), _p(done),
-            _p(agg), _p(r_tr), _p(t_tr), _p(c_tr), _p(f_tr), int(self.nthreads))
+            _p(agg), _p(r_tr), _p(t_tr), _p(c_tr), _p(f_tr), _p(z_tr), _p(Ni_tr), _p(tie_tr), _p(pos_tr),
+            int(self.nthreads))
         if rc != 0:
             raise ValueError(f"oracle_rollout_batch failed rc={rc}")
         return dict(agg=agg, r=r_tr, true_r=t_tr, ncoll=c_tr, finished=f_tr, done=done,
                     pos=self.pos.copy(), vel=self.vel.copy(), z=self.z.copy(), Ni=self.Ni.copy(),
-                    t=self.t.copy())
+                    t=self.t.copy(), z_tr=z_tr, Ni_tr=Ni_tr, tie_tr=tie_tr, pos_tr=pos_tr)
 
 
 def returns(reward_tr, Ni_tr, finished_tr, discount, baseline=None):

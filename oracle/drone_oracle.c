@@ -279,6 +279,10 @@ typedef struct {
     double *agg, *r_tr, *true_tr;
     int32_t *ncoll_tr;
     uint8_t *fin_tr, *done;
+    /* optional per-step observations (what step() returned at every executed step) */
+    double *z_tr, *pos_tr;     /* [T][E][n][(k+1) cols], [T][E][n][2] */
+    int32_t *Ni_tr;            /* [T][E][n][k+1] */
+    uint8_t *tie_tr;           /* [T][E][n]: the row's k nearest contain an exact distance tie */
 } rollout_job;
 
 static void *rollout_worker(void *arg)
@@ -298,7 +302,14 @@ static void *rollout_worker(void *arg)
             integrate_one(n, jb->p, pos, vel, rj->act_stream + ((size_t)t * E + e) * n * 2);
             observe_one(n, k, jb->simplify, jb->p, pos, vel, jb->radius, jb->xF, jb->d_safety, jb->deltas,
                         r, tr, jb->z + (size_t)e * n * (k + 1) * cols, jb->Ni + (size_t)e * n * (k + 1),
-                        jb->ncoll + e, NULL, scratch);
+                        jb->ncoll + e, rj->tie_tr ? rj->tie_tr + ((size_t)t * E + e) * n : NULL, scratch);
+            if (rj->z_tr)
+                memcpy(rj->z_tr + ((size_t)t * E + e) * n * (k + 1) * cols, jb->z + (size_t)e * n * (k + 1) * cols,
+                       sizeof(double) * (size_t)n * (k + 1) * cols);
+            if (rj->Ni_tr)
+                memcpy(rj->Ni_tr + ((size_t)t * E + e) * n * (k + 1), jb->Ni + (size_t)e * n * (k + 1),
+                       sizeof(int32_t) * (size_t)n * (k + 1));
+            if (rj->pos_tr) memcpy(rj->pos_tr + ((size_t)t * E + e) * n * 2, pos, sizeof(double) * (size_t)n * 2);
             const uint8_t fin = finish_one(n, jb->p, pos, jb->xF, jb->t + e);
             jb->finished[e] = fin;
             double mr = 0, mt = 0;
@@ -316,6 +327,14 @@ static void *rollout_worker(void *arg)
     return NULL;
 }
 
+int oracle_rollout_batch_obs(int E, int n, int k, int simplify, int T, const oracle_params *p,
+                             double *pos, double *vel, const double *radius, const double *act_stream,
+                             const double *xF, const double *d_safety, const double *deltas,
+                             double *r, double *true_r, double *z, int32_t *Ni,
+                             int32_t *ncoll, uint8_t *finished, int32_t *t, uint8_t *done,
+                             double *agg, double *r_tr, double *true_tr, int32_t *ncoll_tr, uint8_t *fin_tr,
+                             double *z_tr, int32_t *Ni_tr, uint8_t *tie_tr, double *pos_tr, int nthreads);
+
 int oracle_rollout_batch(int E, int n, int k, int simplify, int T, const oracle_params *p,
                          double *pos, double *vel, const double *radius, const double *act_stream,
                          const double *xF, const double *d_safety, const double *deltas,
@@ -324,9 +343,23 @@ int oracle_rollout_batch(int E, int n, int k, int simplify, int T, const oracle_
                          double *agg, double *r_tr, double *true_tr, int32_t *ncoll_tr, uint8_t *fin_tr,
                          int nthreads)
 {
+    return oracle_rollout_batch_obs(E, n, k, simplify, T, p, pos, vel, radius, act_stream, xF, d_safety, deltas, r,
+                                    true_r, z, Ni, ncoll, finished, t, done, agg, r_tr, true_tr, ncoll_tr, fin_tr,
+                                    NULL, NULL, NULL, NULL, nthreads);
+}
+
+int oracle_rollout_batch_obs(int E, int n, int k, int simplify, int T, const oracle_params *p,
+                             double *pos, double *vel, const double *radius, const double *act_stream,
+                             const double *xF, const double *d_safety, const double *deltas,
+                             double *r, double *true_r, double *z, int32_t *Ni,
+                             int32_t *ncoll, uint8_t *finished, int32_t *t, uint8_t *done,
+                             double *agg, double *r_tr, double *true_tr, int32_t *ncoll_tr, uint8_t *fin_tr,
+                             double *z_tr, int32_t *Ni_tr, uint8_t *tie_tr, double *pos_tr, int nthreads)
+{
     if (E < 0 || n < 1 || k < 0 || k >= n || T < 0) return -1;
     rollout_job proto;
     memset(&proto, 0, sizeof proto);
+    proto.z_tr = z_tr; proto.Ni_tr = Ni_tr; proto.tie_tr = tie_tr; proto.pos_tr = pos_tr;
     batch_job *jb = &proto.jb;
     jb->E = E; jb->n = n; jb->k = k; jb->simplify = simplify; jb->do_step = 1; jb->p = p;
     jb->pos = pos; jb->vel = vel; jb->radius = radius; jb->xF = xF;

@@ -15,6 +15,7 @@ c_void_p, c_int32, c_double = ctypes.c_void_p, ctypes.c_int32, ctypes.c_double
 
 DS_OK, DS_ERR_ARG, DS_ERR_CUDA, DS_ERR_NO_DEVICE, DS_ERR_INTERNAL = 0, -1, -2, -3, -4
 DS_LOG_DIV, DS_LOG_DIFF, DS_LOG_RCP = 0, 1, 2
+DS_HOST_COMPACT_OBS = 1
 DS_CTRL_PROPORTIONAL, DS_CTRL_GRADIENT = 1, 2
 DS_MAX_AGENTS, DS_MAX_K = 1024, 16
 
@@ -87,7 +88,7 @@ class ds_host_step_out(ctypes.Structure):
 
 
 class ds_host_rollout(ctypes.Structure):
-    _fields_ = [("T", c_int32), ("chunk", c_int32), ("n_actions", c_int32), ("_pad", c_int32),
+    _fields_ = [("T", c_int32), ("chunk", c_int32), ("n_actions", c_int32), ("flags", c_int32),
                 ("actions", c_void_p), ("action_idx", c_void_p), ("action_table", c_void_p),
                 ("pos_tr", c_void_p), ("vel_tr", c_void_p), ("reward_tr", c_void_p),
                 ("true_reward_tr", c_void_p), ("z_tr", c_void_p), ("Ni_tr", c_void_p),

@@ -179,6 +179,18 @@ class BatchedDrones:
         _lib.check(self.lib.ds_observe(self._h, ctypes.byref(p), ctypes.byref(self._io), self._stream()),
                    "ds_observe")
 
+    def observe_host(self):
+        """observe(), then the whole result block (state, z, rewards, Ni, collision count) in ONE
+        device->host transfer and one synchronise; returns the numpy views step_host() returns."""
+        self.observe()
+        if self._hblock is None:
+            self._hblock = torch.empty(self._block.numel(), dtype=torch.uint8, pin_memory=True)
+            self._hviews = {name: self._piece(self._hblock, name).numpy() for name in self._layout}
+        with torch.cuda.device(self.device):
+            self._hblock.copy_(self._block, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        return self._hviews
+
     def set_state(self, state, internal_t=None):
         """state[E,n,5] rows [x,y,vx,vy,l] (host float64) -> device; observation NOT refreshed."""
         st = np.ascontiguousarray(np.asarray(state, np.float64).reshape(self.n_envs, self.n_agents, 5))
@@ -272,6 +284,30 @@ class BatchedDrones:
         return self._hviews
 
     # ------------------------------------------------------------------ rollout
+    def _snapshot_obs0(self, out, rec):
+        """`record` name "obs_pre": keep the observation the FIRST step of the call is taken from
+        (z_states / Ni of the state before the call).  The trajectory buffers hold the observation
+        AFTER each step (what `env.step` returns, drone_env.py:258); the reference's learners pair
+        step t with the observation BEFORE it (train_problem.py:84-96 stores `z_states`, `Ni` read
+        before `env.step`; SAC_agents.py:333-346) -- see pre_step_observations()."""
+        if "obs_pre" in rec:
+            out["z0"] = self.z_states.clone()
+            out["Ni0"] = self.Ni.clone()
+
+    @staticmethod
+    def pre_step_observations(out):
+        """(z_pre, Ni_pre) [T,E,n,...]: the observation each recorded step was TAKEN FROM, i.e.
+        z_pre[t] = z(s_t), Ni_pre[t] = N(s_t): the pre-call snapshot followed by the recorded
+        post-step observations shifted by one step.  This -- not out["Ni"] -- is what the reference's
+        train_NN sums its advantages over (buffers[i][t].Ni = N_i(s_t), SAC_agents.py:333-346) and what
+        the actor that produced action t was fed (log_p_of_a, utils.py:311-318).  Needs a rollout
+        recorded with "obs" and "obs_pre"."""
+        if "z0" not in out or "z" not in out:
+            raise KeyError('record the rollout with ("obs", "obs_pre") to rebuild the pre-step observations')
+        z_pre = torch.cat([out["z0"].unsqueeze(0), out["z"][:-1]], 0)
+        Ni_pre = torch.cat([out["Ni0"].unsqueeze(0), out["Ni"][:-1]], 0)
+        return z_pre, Ni_pre
+
     def rollout(self, actions=None, action_idx=None, action_table=None, record=("reward", "true_reward",
                 "ncoll", "finished"), out=None):
         """T fused steps in ONE launch (ds_rollout).
@@ -301,6 +337,7 @@ class BatchedDrones:
             return t
 
         rec = set(record)
+        self._snapshot_obs0(out, rec)
         ro = _lib.ds_rollout_io()
         ro.T = T
         ro.n_actions = 0 if action_table is None else int(action_table.shape[0])
@@ -344,6 +381,7 @@ class BatchedDrones:
             return t
 
         rec = set(record)
+        self._snapshot_obs0(out, rec)
         ro = _lib.ds_rollout_io()
         ro.T = int(T)
         if "pos" in rec: ro.pos_tr = buf("pos", (T, E, n, 2), dt_).data_ptr()
@@ -366,31 +404,50 @@ class BatchedDrones:
 
     def rollout_host(self, actions=None, action_idx=None, action_table=None,
                      record=("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished"),
-                     chunk=0, out=None):
+                     chunk=0, out=None, compact=False):
         """End-to-end episode loop with HOST buffers (ds_rollout_host): pinned host action stream
         in, pinned host trajectories out, copies pipelined against the kernel.  `actions` /
-        `action_idx` must be pinned CPU tensors (or are copied into pinned staging).  out["vel"]
-        is a view of the action stream when explicit actions are given."""
+        `action_idx` are used in place when they are pinned, contiguous CPU tensors of this
+        environment's dtype and shape [T,E,n,2] / uint8 [T,E,n]; anything else is copied into pinned
+        staging first.  out["vel"] is a view of the action stream when explicit actions are given.
+        compact=True: out["z"] comes back as float32 (what the reference's actors cast it to,
+        utils.py:305) and out["Ni"] as uint8 (255 = none): less than half the observation bytes
+        across PCIe.
+        One call = one episode segment from the CURRENT state with done = 0 and fresh episode sums
+        (returned in out["agg"]); self.done / self.agg are not touched: an environment that finishes
+        stops for the rest of the call only (its vel rows past the end still echo the actions)."""
         E, n, k = self.n_envs, self.n_agents, self.k_closest
         hr = _lib.ds_host_rollout()
         keep = []
+
+        def usable(t, dtype, tail):
+            return (isinstance(t, torch.Tensor) and not t.is_cuda and t.is_pinned() and t.dtype == dtype and
+                    t.is_contiguous() and t.dim() == len(tail) + 1 and tuple(t.shape[1:]) == tail)
+
         if actions is not None:
-            a = actions if (isinstance(actions, torch.Tensor) and actions.is_pinned()) else None
+            a = actions if usable(actions, self.dtype, (E, n, 2)) else None
             if a is None:
-                a = self._pin("ro_act", tuple(np.shape(actions)), self.dtype)
-                a.copy_(torch.as_tensor(np.asarray(actions)))
+                src = torch.as_tensor(np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions))
+                if tuple(src.shape[1:]) != (E, n, 2):
+                    raise ValueError(f"actions must have shape [T,{E},{n},2]")
+                a = self._pin("ro_act", tuple(src.shape), self.dtype)
+                a.copy_(src)
             T = a.shape[0]
             hr.actions = a.data_ptr(); keep.append(a)
         else:
-            a = action_idx if (isinstance(action_idx, torch.Tensor) and action_idx.is_pinned()) else None
+            a = action_idx if usable(action_idx, torch.uint8, (E, n)) else None
             if a is None:
-                a = self._pin("ro_aidx", tuple(np.shape(action_idx)), torch.uint8)
-                a.copy_(torch.as_tensor(np.asarray(action_idx)))
+                src = torch.as_tensor(np.asarray(action_idx.cpu() if isinstance(action_idx, torch.Tensor) else action_idx))
+                if tuple(src.shape[1:]) != (E, n):
+                    raise ValueError(f"action_idx must have shape [T,{E},{n}]")
+                a = self._pin("ro_aidx", tuple(src.shape), torch.uint8)
+                a.copy_(src)
             T = a.shape[0]
             tab = torch.as_tensor(np.asarray(action_table), dtype=self.dtype).contiguous()
             hr.action_idx = a.data_ptr(); hr.action_table = tab.data_ptr(); hr.n_actions = tab.shape[0]
             keep += [a, tab]
         hr.T, hr.chunk = T, int(chunk)
+        hr.flags = _lib.DS_HOST_COMPACT_OBS if compact else 0
         out = {} if out is None else out
         rec = set(record)
 
@@ -413,8 +470,8 @@ class BatchedDrones:
         if "reward" in rec: hr.reward_tr = hbuf("reward", (T, E, n), dt_)
         if "true_reward" in rec: hr.true_reward_tr = hbuf("true_reward", (T, E, n), dt_)
         if "obs" in rec:
-            hr.z_tr = hbuf("z", (T, E, n, k + 1, self.cols), dt_)
-            hr.Ni_tr = hbuf("Ni", (T, E, n, k + 1), torch.int32)
+            hr.z_tr = hbuf("z", (T, E, n, k + 1, self.cols), torch.float32 if compact else dt_)
+            hr.Ni_tr = hbuf("Ni", (T, E, n, k + 1), torch.uint8 if compact else torch.int32)
         if "ncoll" in rec: hr.ncoll_tr = hbuf("ncoll", (T, E), torch.int32)
         if "finished" in rec: hr.finished_tr = hbuf("finished", (T, E), torch.uint8)
         hr.agg = hbuf("agg", (E, 4), torch.float64)
@@ -426,9 +483,13 @@ class BatchedDrones:
     def returns(self, reward, Ni, finished, discount=0.99, baseline=None, out=None):
         """Monte-Carlo returns G_i(t) and Delta-neighbourhood advantage sums
         sum_{j in N_i(t)} (G_j(t) - V_i(t)) of a recorded rollout, on the device (ds_returns;
-        reference SAC_agents.py:304-310, 333-345).  reward [T,E,n], Ni [T,E,n,k+1] and
-        finished [T,E] are the trajectory tensors rollout() records ('reward', 'Ni', 'finished');
-        baseline [T,E,n] is the critic's V (None = 0).  Returns dict(returns, advantage, count)."""
+        reference SAC_agents.py:304-310, 333-345).  reward [T,E,n] and finished [T,E] are the
+        trajectory tensors rollout() records.  Ni [T,E,n,k+1] must be the neighbour lists of the
+        state each step was TAKEN FROM, N_i(s_t) -- the reference stores `Ni = env.Ni` BEFORE
+        `env.step` (train_problem.py:84-96) -- i.e. pre_step_observations(out)[1], NOT out["Ni"]
+        (which holds N_i(s_{t+1}), the observation step t returned); likewise baseline [T,E,n] is
+        the critic's V_i(z_i(s_t)) on pre_step_observations(out)[0] (None = 0).
+        returns_from_rollout() does the shift.  Returns dict(returns, advantage, count)."""
         E, n, k = self.n_envs, self.n_agents, self.k_closest
         T = reward.shape[0]
         assert tuple(reward.shape) == (T, E, n) and reward.dtype == self.dtype and reward.is_cuda
@@ -456,6 +517,14 @@ class BatchedDrones:
         io.count = buf("count", torch.uint8).data_ptr()
         _lib.check(self.lib.ds_returns(self._h, ctypes.byref(io), self._stream()), "ds_returns")
         return out
+
+    def returns_from_rollout(self, ro, discount=0.99, critic=None, out=None):
+        """train_NN's returns and advantage sums (SAC_agents.py:304-310, 333-346) of a rollout
+        recorded with ("reward", "obs", "obs_pre", "finished"): neighbour lists and critic inputs
+        are the PRE-step observations.  critic: callable z_pre [T,E,n,(k+1)*cols] -> V [T,E,n], or None."""
+        z_pre, Ni_pre = self.pre_step_observations(ro)
+        base = None if critic is None else critic(z_pre.flatten(-2))
+        return self.returns(ro["reward"], Ni_pre, ro["finished"], discount=discount, baseline=base, out=out)
 
     # ------------------------------------------------------------------ policy
     def load_policy(self, W1, b1, W2, b2, W3, b3, action_table):
@@ -518,6 +587,7 @@ class BatchedDrones:
             return t
 
         rec = set(record)
+        self._snapshot_obs0(out, rec)
         ro = _lib.ds_rollout_io()
         ro.T = int(T)
         if "pos" in rec: ro.pos_tr = buf("pos", (T, E, n, 2), dt_).data_ptr()

@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -68,6 +70,7 @@ struct ds_handle {
         void *act = nullptr; uint8_t *aidx = nullptr;
         void *pos = nullptr, *r = nullptr, *tr = nullptr, *z = nullptr;
         int32_t *Ni = nullptr, *ncoll = nullptr; uint8_t *fin = nullptr;
+        float *zf = nullptr; uint8_t *Ni8 = nullptr;      // compact copies for the host (DS_HOST_COMPACT_OBS)
         cudaEvent_t h2d_done = nullptr, kernel_done = nullptr, d2h_done = nullptr;
     } slot[2];
     int slot_chunk = 0;           // steps the slots are sized for
@@ -253,7 +256,7 @@ void plan_launch(ds_handle *h)
         bestTC = bestTC > tcmax ? tcmax : bestTC;
     }
     const int og = env_int("DS_PLAN_G", 0), otc = env_int("DS_PLAN_TC", 0);
-    if (og > 0 && otc > 0 && og * n * otc <= cap) { bestG = clampG(og); bestTC = otc; }
+    if (og > 0 && otc > 0 && otc <= 32 && og * n * otc <= cap) { bestG = clampG(og); bestTC = otc; }   // ngbits holds <= 32 slices
     h->ro_G = bestG; h->ro_TC = bestTC;
     h->ro_threads = ((bestG * n * bestTC + 31) / 32) * 32;
     h->ro_blocks = (int)(((long long)E + bestG - 1) / bestG);
@@ -302,13 +305,32 @@ int fill_step_args(ds_handle *h, const ds_params *p, const ds_buffers *io, const
 
 struct Geom { int blocks, threads; size_t smem; };
 
+// Function attributes are per (device, kernel): set them when they change, not on every launch
+// (two driver calls per launch were most of the host time of the one-environment drop-in step).
+int ensure_attrs(const void *kernel, size_t smem, int carveout)
+{
+    struct Cfg { size_t smem; int carve; };
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, Cfg> done;
+    int dev = 0;
+    DS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev, kernel);
+    auto it = done.find(key);
+    if (it != done.end() && it->second.smem >= smem && it->second.carve == carveout) return DS_OK;
+    const size_t want = (it != done.end() && it->second.smem > smem) ? it->second.smem : smem;
+    if (want > 48 * 1024)
+        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+    // residency is shared-memory bound for small CTAs: ask for the largest carve-out (default)
+    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    done[key] = Cfg{want, carveout};
+    return DS_OK;
+}
+
 template <typename KernelT, typename ArgsT>
 int launch(KernelT kernel, const ArgsT &args, const Geom &gm, cudaStream_t st, int carveout = cudaSharedmemCarveoutMaxShared)
 {
-    if (gm.smem > 48 * 1024)
-        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gm.smem));
-    // residency is shared-memory bound for small CTAs: ask for the largest carve-out (default)
-    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+    if (int rc = ensure_attrs(reinterpret_cast<const void *>(kernel), gm.smem, carveout)) return rc;
     kernel<<<gm.blocks, gm.threads, gm.smem, st>>>(args);
     DS_CUDA(cudaGetLastError());
     return DS_OK;
@@ -399,10 +421,7 @@ template <typename Real, int N>
 int launch_rollout2_n(ds_handle *h, const ds::Ro2Args &a, const CUtensorMap &tm, cudaStream_t st)
 {
     auto kernel = ds::rollout2_kernel<Real, N, 2>;
-    if (h->ro2_smem > 48 * 1024)
-        DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ro2_smem));
-    // the per-warp blocks need ~24 KB per CTA: leave the rest of the 256 KB to L1 (log table, spills)
-    DS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, env_int("DS_RO2_CARVE", 100)));
+    if (int rc = ensure_attrs(reinterpret_cast<const void *>(kernel), h->ro2_smem, env_int("DS_RO2_CARVE", 100))) return rc;
     if (env_int("DS_PLAN_DEBUG", 0)) {
         int nb = -1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, h->ro2_threads, h->ro2_smem);
@@ -480,12 +499,27 @@ void free_slots(ds_handle *h)
     for (auto &s : h->slot) {
         cudaFree(s.act); cudaFree(s.aidx); cudaFree(s.pos); cudaFree(s.r);
         cudaFree(s.tr); cudaFree(s.z); cudaFree(s.Ni); cudaFree(s.ncoll); cudaFree(s.fin);
+        cudaFree(s.zf); cudaFree(s.Ni8);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.kernel_done) cudaEventDestroy(s.kernel_done);
         if (s.d2h_done) cudaEventDestroy(s.d2h_done);
         s = ds_handle::Slot();
     }
     h->slot_chunk = 0; h->slot_mask = 0;
+}
+
+// Host-facing compaction of a chunk's observations (ds_rollout_host, DS_HOST_COMPACT_OBS): z as float32
+// -- what the reference's actors cast it to (utils.py:305) -- and the neighbour lists as u8 (255 = none).
+template <typename Real>
+__global__ void compact_obs_kernel(const Real *__restrict__ z, const int *__restrict__ Ni, float *__restrict__ zf,
+                                   uint8_t *__restrict__ Ni8, size_t nz, size_t nn)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nz; q += stride) zf[q] = (float)z[q];
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nn; q += stride) {
+        const int v = Ni[q];
+        Ni8[q] = v < 0 ? (uint8_t)255 : (uint8_t)v;
+    }
 }
 
 struct DeviceGuard {
@@ -625,7 +659,7 @@ try {
 
 int ds_control(ds_handle *h, int controller, double u_max, const ds_buffers *io, void *actions_out_dev,
                void *cuda_stream)
-{
+try {
     ds_params p;
     ds_default_params(&p);
     ds::StepArgs a;
@@ -637,6 +671,10 @@ int ds_control(ds_handle *h, int controller, double u_max, const ds_buffers *io,
     a.ctrl = controller; a.u_max = u_max; a.ctrl_out = actions_out_dev;
     DeviceGuard guard(h->device);
     return launch_step(h, a, (cudaStream_t)cuda_stream);
+} catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
+    return fail(DS_ERR_INTERNAL, std::string("ds_control: host exception: ") + ex.what());
+} catch (...) {
+    return fail(DS_ERR_INTERNAL, "ds_control: unknown host exception");
 }
 
 static int launch_rollout_control(ds_handle *h, const ds::RolloutArgs &ra, const Geom &gm, cudaStream_t st)
@@ -713,7 +751,12 @@ try {
     // the kernel indexes trajectory elements with 32 bits: split calls whose T * E * n does not fit
     const size_t EN = (size_t)h->E * h->n, E = (size_t)h->E, rb = (size_t)h->real_bytes;
     const size_t zc = (size_t)(h->k + 1) * (h->simplify ? 2 : 5);
-    const int max_T = (int)std::max<size_t>(1, (((size_t)1 << 32) - 1) / EN - (size_t)h->ro_TC);
+    // (signed 64-bit: E * n * (TC + 1) may exceed 2^32, which a size_t subtraction would wrap)
+    const long long slack = (long long)((((size_t)1 << 32) - 1) / EN) - (long long)std::max(h->ro_TC, 32);
+    if (slack < 1)
+        return fail(DS_ERR_ARG, "ds_rollout: n_envs * n_agents too large for the kernel's 32-bit trajectory indices; "
+                                "split the batch over several handles");
+    const int max_T = (int)std::min<long long>(slack, 1 << 30);
     auto off = [](const void *p, size_t bytes) -> void * { return p ? (char *)p + bytes : nullptr; };
     for (int t0 = 0; t0 < ro->T; t0 += max_T) {
         const size_t ts = (size_t)t0;
@@ -1201,7 +1244,10 @@ try {
     // supplied, so it is written on the host while the pipeline drains and never crosses PCIe
     if (hr->reward_tr) { out_step += A * rb; mask |= 8u; }
     if (hr->true_reward_tr) { out_step += A * rb; mask |= 16u; }
-    if (hr->z_tr) { out_step += A * zc * rb + A * (h->k + 1) * 4; mask |= 32u; }
+    const bool compact = (hr->flags & DS_HOST_COMPACT_OBS) != 0;
+    if (compact && h->n > 255) return fail(DS_ERR_ARG, "ds_rollout_host: DS_HOST_COMPACT_OBS needs n_agents <= 255");
+    if (hr->z_tr) { out_step += compact ? A * zc * 4 + A * (h->k + 1) : A * zc * rb + A * (h->k + 1) * 4; mask |= 32u; }
+    if (compact) mask |= 256u;
     if (hr->ncoll_tr) { out_step += E * 4; mask |= 64u; }
     if (hr->finished_tr) { out_step += E; mask |= 128u; }
     int chunk = hr->chunk;
@@ -1234,6 +1280,10 @@ try {
             if (hr->z_tr) {
                 DS_CUDA(cudaMalloc(&s.z, c * A * zc * rb));
                 DS_CUDA(cudaMalloc(&s.Ni, c * A * (h->k + 1) * 4));
+                if (compact) {
+                    DS_CUDA(cudaMalloc((void **)&s.zf, c * A * zc * 4));
+                    DS_CUDA(cudaMalloc((void **)&s.Ni8, c * A * (h->k + 1)));
+                }
             }
             if (hr->ncoll_tr) DS_CUDA(cudaMalloc(&s.ncoll, c * E * 4));
             if (hr->finished_tr) DS_CUDA(cudaMalloc(&s.fin, c * E));
@@ -1277,6 +1327,13 @@ try {
         ro.z_tr = s.z; ro.Ni_tr = s.Ni; ro.ncoll_tr = s.ncoll; ro.finished_tr = s.fin;
         ro.agg = h->d_agg; ro.done = h->d_done;
         if (int rc = ds_rollout(h, p, io, &ro, cuda_stream)) return rc;
+        if (compact && hr->z_tr) {
+            const size_t nz = tcs * A * zc, nn = tcs * A * (h->k + 1);
+            const int blocks = 4 * h->sm_count;
+            if (rb == 8) compact_obs_kernel<double><<<blocks, 256, 0, st>>>((const double *)s.z, s.Ni, s.zf, s.Ni8, nz, nn);
+            else compact_obs_kernel<float><<<blocks, 256, 0, st>>>((const float *)s.z, s.Ni, s.zf, s.Ni8, nz, nn);
+            DS_CUDA(cudaGetLastError());
+        }
         DS_CUDA(cudaEventRecord(s.kernel_done, st));
         // D2H
         DS_CUDA(cudaStreamWaitEvent(h->s_d2h, s.kernel_done, 0));
@@ -1284,7 +1341,10 @@ try {
         if (hr->pos_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->pos_tr + t0s * A * 2 * rb, s.pos, tcs * A * 2 * rb, cudaMemcpyDeviceToHost, d));
         if (hr->reward_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->reward_tr + t0s * A * rb, s.r, tcs * A * rb, cudaMemcpyDeviceToHost, d));
         if (hr->true_reward_tr) DS_CUDA(cudaMemcpyAsync((char *)hr->true_reward_tr + t0s * A * rb, s.tr, tcs * A * rb, cudaMemcpyDeviceToHost, d));
-        if (hr->z_tr) {
+        if (hr->z_tr && compact) {
+            DS_CUDA(cudaMemcpyAsync((char *)hr->z_tr + t0s * A * zc * 4, s.zf, tcs * A * zc * 4, cudaMemcpyDeviceToHost, d));
+            DS_CUDA(cudaMemcpyAsync((char *)hr->Ni_tr + t0s * A * (h->k + 1), s.Ni8, tcs * A * (h->k + 1), cudaMemcpyDeviceToHost, d));
+        } else if (hr->z_tr) {
             DS_CUDA(cudaMemcpyAsync((char *)hr->z_tr + t0s * A * zc * rb, s.z, tcs * A * zc * rb, cudaMemcpyDeviceToHost, d));
             DS_CUDA(cudaMemcpyAsync(hr->Ni_tr + t0s * A * (h->k + 1), s.Ni, tcs * A * (h->k + 1) * 4, cudaMemcpyDeviceToHost, d));
         }

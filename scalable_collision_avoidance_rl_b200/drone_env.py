@@ -139,12 +139,9 @@ class drones:
         eng = self._engine(end_points, d_safety, deltas)
         self._synced = None                              # the device state is overwritten below
         eng.set_state(np.asarray(state, np.float64)[None], internal_t=self.internal_t)
-        eng.observe()
-        r = eng.rewards[0].cpu().numpy()
-        tr = eng.true_rewards[0].cpu().numpy()
-        ncoll = np.int64(eng.n_collisions[0].item())
-        z_states, Ni = self._unpack_obs(eng.z_states[0].cpu().numpy(), eng.Ni[0].cpu().numpy())
-        return r, ncoll, z_states, Ni, tr
+        out = eng.observe_host()                          # one transfer of the whole result block, one synchronise
+        z_states, Ni = self._unpack_obs(out["z"][0], out["Ni"][0])
+        return np.array(out["r"][0]), np.int64(out["nc"][0]), z_states, Ni, np.array(out["tr"][0])
 
     # ------------------------------------------------------------------ hot path
     def step(self, actions):
@@ -188,13 +185,21 @@ class drones:
             ax.plot(xF[i, 0], xF[i, 1], marker="x", color=colour)
         for o in self.obstacles:
             ax.add_patch(plt.Circle((o[0], o[1]), o[2], color=BLACK))
-        if not_animate:
+        if not_animate:                                   # reference drone_env.py:430-433: show, or hand the figure back
             plt.show()
-        return fig, ax
+        else:
+            return fig
 
-    def animate_basic(self, trajectory, frame_time=0.2):
+    def animate_basic(self, trajectory, frame_time=0.2, frames=20):
+        """reference drone_env.py:436-448: about `frames` evenly spaced states of the trajectory."""
         plt = _plt()
-        for state in trajectory:
+        good_frame = 0
+        each_frame = len(trajectory) / frames
+        for n_frame, state in enumerate(trajectory):
+            if each_frame > 1 and round(good_frame) == n_frame:
+                good_frame += each_frame
+            else:
+                continue
             self.show(state, not_animate=False)
             plt.pause(frame_time)
             plt.close()

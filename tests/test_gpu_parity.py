@@ -258,6 +258,26 @@ def test_host_entries_match_device_entries():
     for key in ("pos", "vel", "reward", "true_reward", "z", "Ni", "ncoll", "finished"):
         assert torch.equal(hh[key], dd[key].cpu()), f"index mode {key}"
     assert np.array_equal(hh["vel"].numpy(), tab[idx])
+    # compact host observations (DS_HOST_COMPACT_OBS): z as float32, Ni as u8 (255 = none); the rest unchanged
+    c3 = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    hc = c3.rollout_host(action_idx=idx, action_table=tab, record=rec, chunk=7, compact=True)
+    torch.cuda.synchronize()
+    assert hc["z"].dtype == torch.float32 and hc["Ni"].dtype == torch.uint8
+    assert torch.equal(hc["z"], dd["z"].cpu().float())
+    ni = dd["Ni"].cpu()
+    assert torch.equal(hc["Ni"], torch.where(ni < 0, torch.full_like(ni, 255), ni).to(torch.uint8))
+    for key in ("pos", "reward", "true_reward", "ncoll", "finished"):
+        assert torch.equal(hc[key], dd[key].cpu()), f"compact mode {key}"
+    # host tensors that cannot be used in place (wrong dtype / not contiguous) are staged, not misread
+    c4 = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=9, warn=False)
+    wide = torch.zeros((T, E, n, 4), dtype=torch.float64).pin_memory()
+    wide[..., :2] = torch.as_tensor(tab[idx])
+    bad = wide[..., :2]                                                  # pinned, right dtype, NOT contiguous
+    assert bad.is_pinned() and not bad.is_contiguous()
+    hb = c4.rollout_host(actions=bad, record=("pos", "reward"), chunk=7)
+    assert torch.equal(hb["pos"], dd["pos"].cpu())
+    with pytest.raises(ValueError):
+        c4.rollout_host(actions=np.zeros((3, E, n + 1, 2)), record=("pos",))
 
 
 @pytest.mark.parametrize("n,grid,delta", [(10, [5, 5], 1.0), (32, [32, 32], 2.5)])
@@ -282,6 +302,88 @@ def test_float32_throughput_mode(n, grid, delta):
     err = np.abs(r.cpu().numpy() - ref.r) / np.maximum(1.0, np.abs(ref.r))
     assert err.max() < 2e-6, err.max()
     assert np.array_equal(ncoll.cpu().numpy(), ref.ncoll)
+
+
+@pytest.mark.parametrize("n,grid,delta,box", [(10, [5, 5], 1.0, None), (10, [5, 5], 1.0, 1.6), (32, [32, 32], 2.5, None)])
+def test_float32_free_running_episode_drift(n, grid, delta, box):
+    """float32 throughput mode FREE-RUNNING a whole 200-step episode (fused rollout, no teacher forcing)
+    against the float64 oracle on the same action stream, lattice starts and dense (colliding) starts
+    (box: all agents in a box of that side).  The stated tolerance of this mode, asserted here:
+      positions   |dx| <= 4e-6 * grid  (200 roundings of ~1 float32 ulp at the coordinate's magnitude,
+                  random-walk accumulation: 2e-5 on the [5,5] grid, 1.3e-4 on [32,32])
+      rewards     |dr| <= 2e-5 * max(1, |r|) on 99.9 % of the rows whose two runs agree on the collision
+                  count, and <= 2e-2 * max(1, |r|) on all of them: the barrier term b log(d_safety / d) has
+                  slope b / d, so a pair a few 1e-4 from contact turns a 1e-5 position error into a 1e-3
+                  reward error (a pair within ~1e-5 of contact flips a 99.9 term: not a rounding error)
+      collisions  per-step totals differ on < 0.1 % of the steps.
+    The measured maxima are printed (pytest -s) and recorded in profiles/r02/f32_drift.txt by
+    tools/gpu_r02_record.sh."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    E, T = 512, 200
+    rng = np.random.default_rng(5)
+    env = BatchedDrones(E, n, grid, "O", 2, np.ones(n) * delta, True, dtype=torch.float32, seed=2, warn=False)
+    if box is not None:
+        st, _ = env.get_state()
+        st[:, :, 0:2] = rng.uniform(1.0, 1.0 + box, (E, n, 2)).astype(np.float32)
+        env.set_state(st, np.zeros(E, np.int32)); env.observe()
+    pos0 = env.pos.cpu().numpy().astype(np.float64)
+    tab = formation.unit_action_table(16)
+    idx = rng.integers(0, 16, (T, E, n))
+    act32 = tab.astype(np.float32)[idx]
+    orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, 2, True,
+                             c_oracle.default_params(env.collision_weight), nthreads=8)
+    orc.set_state(pos0)
+    ref = orc.rollout(act32.astype(np.float64), record_obs=True)
+    out = env.rollout(actions=torch.as_tensor(act32, device=env.device), record=("pos", "reward", "ncoll", "finished"))
+    torch.cuda.synchronize()
+    fin = ref["finished"]
+    assert np.array_equal(out["finished"].cpu().numpy(), fin)
+    live = fin != 2
+    dpos = np.abs(out["pos"].cpu().numpy().astype(np.float64) - ref["pos_tr"])[live].max()
+    nc32, nc64 = out["ncoll"].cpu().numpy(), ref["ncoll"]
+    same = (nc32 == nc64) & live
+    r32, r64 = out["reward"].cpu().numpy().astype(np.float64), ref["r"]
+    rel = (np.abs(r32 - r64) / np.maximum(1.0, np.abs(r64)))[same]
+    mism = 1.0 - same.sum() / live.sum()
+    q999 = float(np.quantile(rel, 0.999))
+    print(f"f32 drift n={n} box={box}: max |dpos| {dpos:.2e}, rel |dr| median {np.median(rel):.2e} p99.9 {q999:.2e} "
+          f"max {rel.max():.2e}, collision-count mismatches {100 * mism:.4f} % of steps, "
+          f"collisions seen {int(nc64[live].sum())}")
+    assert dpos <= 4e-6 * max(5.0, float(grid[0]))
+    assert q999 <= 2e-5 * max(1.0, grid[0] / 5.0) and rel.max() <= 2e-2
+    assert mism < 1e-3
+    if box is not None:
+        assert nc64[live].sum() > 0
+
+
+def test_log_mode_rcp_within_stated_difference():
+    """DS_LOG_RCP (log(d_safety / d) as -log(d * (1 / d_safety)), no division): rewards within 1e-13 of
+    the DS_LOG_DIV path (stated: <= 3.4e-16 per barrier term, times b = 0.01, times <= n terms), every
+    integer output identical, on a dense 200-step rollout; step kernel and rollout kernel agree bit
+    for bit in this mode too."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation, _lib
+    n, E, T = 10, 256, 200
+    rng = np.random.default_rng(6)
+    act = torch.as_tensor(formation.unit_action_table(16)[rng.integers(0, 16, (T, E, n))], device="cuda")
+    outs = {}
+    for mode in (_lib.DS_LOG_DIV, _lib.DS_LOG_RCP):
+        env = BatchedDrones(E, n, [5, 5], "O", 2, np.ones(n), True, seed=8, warn=False)
+        st, _ = env.get_state()
+        st[:, :, 0:2] = np.random.default_rng(7).uniform(1.0, 3.0, (E, n, 2))
+        env.set_state(st, np.zeros(E, np.int32)); env.log_mode = mode; env.observe()
+        outs[mode] = {k: v.clone() for k, v in env.rollout(actions=act, record=("pos", "reward", "true_reward", "obs",
+                                                                              "ncoll", "finished")).items()}
+        if mode == _lib.DS_LOG_RCP:            # stepping reproduces the fused rollout bit for bit
+            env.set_state(st, np.zeros(E, np.int32)); env.observe()
+            for t in range(3):
+                _, _, r, nc, _, tr = env.step(act[t])
+                assert torch.equal(r, outs[mode]["reward"][t]) and torch.equal(tr, outs[mode]["true_reward"][t])
+    a, b = outs[_lib.DS_LOG_DIV], outs[_lib.DS_LOG_RCP]
+    for key in ("pos", "Ni", "ncoll", "finished"):
+        assert torch.equal(a[key], b[key]), key
+    assert (a["ncoll"] > 0).any()
+    assert (a["reward"] - b["reward"]).abs().max().item() <= 1e-13
+    assert (a["true_reward"] - b["true_reward"]).abs().max().item() <= 1e-13
 
 
 def test_float32_handle_side_paths():
@@ -376,11 +478,11 @@ def test_full_size_properties():
     assert int(env.n_collisions.sum()) == int(ref.ncoll.sum())
 
 
-FULL = [  # BASELINE.json configs 2-5 at their full batch sizes; T bounded by the oracle's time
+FULL = [  # BASELINE.json configs 2-5 at their full batch sizes, whole 200-step episodes
     ("config2", 5, 4096, [5, 5], 1.0, 200),
     ("config3", 10, 4096, [5, 5], 1.0, 200),
-    ("config4", 32, 8192, [32, 32], 2.5, 40),
-    ("config5", 128, 1024, [64, 64], 1.0, 24),
+    ("config4", 32, 8192, [32, 32], 2.5, 200),
+    ("config5", 128, 1024, [64, 64], 1.0, 200),
 ]
 
 
@@ -398,12 +500,20 @@ def test_rollout_full_size_vs_oracle(name, n, E, grid, delta, T):
     orc = c_oracle.OracleEnv(E, n, env.end_points, env.d_safety, env.deltas, None, 2, True,
                              c_oracle.default_params(env.collision_weight), nthreads=16)
     orc.set_state(start)
-    ref = orc.rollout(act)
+    ref = orc.rollout(act, record_obs=True)
     rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
     out = env.rollout(actions=torch.as_tensor(act, device=env.device), record=rec)
     torch.cuda.synchronize()
     assert np.array_equal(out["finished"].cpu().numpy(), ref["finished"])
     live = ref["finished"] != 2
+    # EVERY step of the fused rollout against the oracle: positions bit-exact, observations and
+    # neighbour lists tie-aware (in slabs of steps to bound the host memory of the comparison)
+    for t0 in range(0, T, 25):
+        sl = slice(t0, min(T, t0 + 25))
+        lv = live[sl]
+        assert np.array_equal(out["pos"][sl].cpu().numpy()[lv], ref["pos_tr"][sl][lv]), f"positions, steps {t0}.."
+        compare_obs(out["z"][sl].cpu().numpy()[lv], out["Ni"][sl].cpu().numpy()[lv], ref["z_tr"][sl][lv],
+                    ref["Ni_tr"][sl][lv], ref["tie_tr"][sl][lv], FP64_TOL, f"{name} steps {t0}..")
     assert_close(out["reward"].cpu().numpy()[live], ref["r"][live], FP64_TOL, "reward")
     assert_close(out["true_reward"].cpu().numpy()[live], ref["true_r"][live], FP64_TOL, "true reward")
     assert np.array_equal(out["ncoll"].cpu().numpy()[live], ref["ncoll"][live]), "collision counts"
@@ -506,6 +616,51 @@ def test_returns_on_rollout_vs_oracle(n, E, k, T):
     assert np.array_equal(out["returns"].cpu().numpy(), G)
     assert np.array_equal(out["advantage"].cpu().numpy(), adv)
     assert np.array_equal(out["count"].cpu().numpy(), cnt)
+
+
+def test_returns_recipe_pairs_steps_with_pre_step_neighbour_lists():
+    """The documented recipe (rollout with "obs_pre" -> returns_from_rollout) against the reference's
+    episode loop restated step by step: `Ni = env.Ni` is read BEFORE `env.step` (train_problem.py:84-96)
+    and train_NN sums the advantages of step t over that list (SAC_agents.py:333-346).  The stepping
+    side records the pre-step lists itself; the rollout side must rebuild them from the post-step
+    trajectory and the pre-call snapshot."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    n, E, T, k = 6, 37, 40, 2
+    rng = np.random.default_rng(11)
+    mk = lambda: BatchedDrones(E, n, [5, 5], "O", k, np.ones(n) * 0.9, True, seed=9, warn=False)
+    a, b = mk(), mk()
+    st, _ = a.get_state()
+    st[:, :, 0:2] = rng.uniform(1.0, 3.5, (E, n, 2))                 # dense: neighbour lists change from step to step
+    tt = rng.integers(150, 200, E).astype(np.int32)                  # some episodes end inside the rollout
+    for env in (a, b):
+        env.set_state(st, tt); env.observe()
+    act = formation.unit_action_table(16)[rng.integers(0, 16, (T, E, n))]
+    act_d = torch.as_tensor(act, device=a.device)
+    # the reference's loop, one step at a time: lists read before the step
+    Ni_pre, z_pre, rew, fin = [], [], [], []
+    done = np.zeros(E, bool)
+    for t in range(T):
+        Ni_pre.append(a.Ni.cpu().numpy().copy()); z_pre.append(a.z_states.cpu().numpy().copy())
+        _, _, r, _, f, _ = a.step(act_d[t])
+        torch.cuda.synchronize()
+        rew.append(r.cpu().numpy().copy())
+        code = np.where(done, 2, f.cpu().numpy())
+        fin.append(code.astype(np.uint8)); done |= f.cpu().numpy().astype(bool)
+    Ni_pre, z_pre, rew, fin = map(np.stack, (Ni_pre, z_pre, rew, fin))
+    V = rng.standard_normal((T, E, n))
+    G, adv, cnt = c_oracle.returns(rew, Ni_pre, fin, 0.97, V)
+    # the fused rollout + the documented recipe
+    ro = b.rollout(actions=act_d, record=("reward", "obs", "obs_pre", "finished"))
+    zp, Np = b.pre_step_observations(ro)
+    out = b.returns_from_rollout(ro, discount=0.97, critic=lambda z: torch.as_tensor(V, device=b.device))
+    torch.cuda.synchronize()
+    ex = fin != 2
+    assert (fin == 2).any() and np.array_equal(ro["finished"].cpu().numpy(), fin)
+    assert np.array_equal(Np.cpu().numpy()[ex], Ni_pre[ex]) and np.array_equal(zp.cpu().numpy()[ex], z_pre[ex], equal_nan=True)
+    assert not np.array_equal(ro["Ni"].cpu().numpy()[ex], Ni_pre[ex]), "post-step lists differ: the shift matters here"
+    assert np.array_equal(out["returns"].cpu().numpy()[ex], G[ex])
+    assert np.array_equal(out["advantage"].cpu().numpy()[ex], adv[ex])
+    assert np.array_equal(out["count"].cpu().numpy()[ex], cnt[ex])
 
 
 @pytest.mark.parametrize("name,ctrl", [("control_gradient_n5", "gradient"), ("control_gradient_n10", "gradient"),
