@@ -282,6 +282,34 @@ def run_reference(args, wl):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def pin_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores NVML reports as local to its GPU, so that the pinned host
+    buffers of the end-to-end leg (allocated afterwards, first-touch) sit on the GPU's NUMA node and
+    the D2H copies do not cross the socket interconnect.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            try:
+                phys = int(vis.split(",")[index])
+            except ValueError:
+                phys = index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < ncpu]
+        orig = sorted(os.sched_getaffinity(0))
+        allowed = sorted(set(cpus) & set(orig))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"cpus": len(allowed), "of": ncpu, "_orig": orig}
+        return {"cpus": 0, "of": ncpu, "note": "no local cores reported"}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {ex}"}
+
+
 class GpuLeg:
     """W warm-up + K timed episodes of one workload on this rank's GPU.  Everything the timed
     region touches (action streams, trajectory buffers, the library's launch plan) exists before
@@ -309,6 +337,10 @@ class GpuLeg:
             self.actions.append(ttab[idx.long()].contiguous())   # [T,E,n,2] Real
             del idx
         self.out = {}
+        # ds_reset_random: draws + start observation in one launch for n <= 32, k = 2 (else two launches)
+        self.reset_launches = 1 if (n <= 32 and K_CLOSEST == 2 and os.environ.get("DS_RESET_FUSED", "1") != "0") else 2
+        self.agg_ring = [torch.zeros(5, dtype=torch.float64, device=dev) for _ in range(4)]
+        self.agg_work = [None] * 4
         self.seed = seed + rank
         self.ep = 0
         self.launches = 0
@@ -321,7 +353,7 @@ class GpuLeg:
         device-side reduction of the episode aggregates (+ the all-reduce)."""
         torch = self.torch
         b = self.ep % self.n_bufs
-        self.env.reset_random(seed=self.seed, stream=self.ep); self.launches += 2
+        self.env.reset_random(seed=self.seed, stream=self.ep); self.launches += self.reset_launches
         if timed:
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(self.stream)
@@ -329,14 +361,29 @@ class GpuLeg:
         if timed:
             e1.record(self.stream)
             self.events.append((e0, e1))
-        agg = self.env.episode_aggregates(); self.launches += 1     # device-side reduce, no host sync
+        # device-side reduce into one of a ring of result vectors, no host sync; the all-reduce of the
+        # 5 doubles runs on NCCL's stream behind it: the next episode does not wait for it
+        slot = self.ep % len(self.agg_ring)
+        if self.agg_work[slot] is not None:
+            self.agg_work[slot].wait()
+            self.agg_work[slot] = None
+        agg = self.env.episode_aggregates(out=self.agg_ring[slot]); self.launches += 1
         if self.world > 1 and allreduce:
             from scalable_collision_avoidance_rl_b200 import dist as dsdist
-            dsdist.allreduce_episode_aggregates(agg)
+            self.agg_work[slot] = dsdist.allreduce_episode_aggregates(agg, async_op=True)
         self.ep += 1
         return agg
 
+    def drain(self):
+        """The launch stream waits for every all-reduce still in flight (inside the timed region: the
+        last episodes' aggregates belong to the K steps)."""
+        for q, w in enumerate(self.agg_work):
+            if w is not None:
+                w.wait()
+                self.agg_work[q] = None
+
     def barrier(self):
+        self.drain()
         if self.world > 1:
             import torch.distributed as dist
             dist.barrier()
@@ -357,6 +404,7 @@ class GpuLeg:
         g0.record(self.stream)
         for _ in range(K):
             self.episode(True)
+        self.drain()
         g1.record(self.stream)
         self.barrier()
         ms = g0.elapsed_time(g1)
@@ -372,6 +420,7 @@ class GpuLeg:
         sum of the per-rank vectors gathered separately, and the step count N * E * T (no environment
         of a random walk reaches its goal formation)."""
         torch = self.torch
+        self.barrier()
         agg = self.episode(False, allreduce=False).clone()
         want_steps = float(self.E * self.T)
         ok_local = abs(float(agg[3].item()) - want_steps) < 0.5 and float(agg[4].item()) == float(self.E)
@@ -424,6 +473,7 @@ def run_ours(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = pin_to_gpu_numa_node(local)     # before any pinned allocation: host buffers land next to the GPU
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -445,7 +495,7 @@ def run_ours(args, wl):
 
     # end to end through the public host API: pinned host action stream in, pinned host
     # trajectories of the reference's 6-tuple out, copies inside the timed region
-    e2e = None
+    e2e = e2e_full = None
     if not args.no_e2e:
         from scalable_collision_avoidance_rl_b200 import formation
         env = leg.env
@@ -454,43 +504,50 @@ def run_ours(args, wl):
             h_act[b].copy_(leg.actions[b])
         rng = np.random.default_rng(99 + rank)
         h_start = formation.sample_start_batched(2 * E, n, grid, rng).reshape(2, E, n, 2)
-        hout = {}
         e2e_steps = max(10, min(K, 50)) if T >= EPISODE else max(2, min(K, 10))
-
-        def e2e_run(total):
-            for ep in range(total):
-                env.reset(h_start[ep % 2])                           # H2D of the start state + observe
-                env.rollout_host(actions=h_act[ep % 2], record=RECORD, out=hout, **leg_e2e_kwargs(args))
-
-        e2e_run(2)
-        leg.barrier()
-        t0 = time.perf_counter()
-        e2e_run(e2e_steps)
-        leg.barrier()
-        el_local = time.perf_counter() - t0
-        el = torch.tensor([el_local], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
         A = E * n
         zc = (K_CLOSEST + 1) * 2
-        zb = 4 if args.e2e_compact else rb
-        nib = 1 if args.e2e_compact else 4
-        d2h = A * (2 * rb + rb + rb + zc * zb + nib * (K_CLOSEST + 1)) + E * 5
-        h2d = A * 2 * rb
-        e2e = {"value": world * E * n * T * e2e_steps / float(el.item()), "unit": "agent-steps/s",
-               # per bench step (= one episode of T env-steps)
-               "h2d_bytes_per_step": h2d * T + A * 2 * 8,
-               # pos, r, true_r, z, Ni, ncoll, finished; vel (= the action, drone_env.py:238) is returned
-               # as a view of the host action stream and does not cross PCIe
-               "d2h_bytes_per_step": d2h * T + E * 4 * 8,
-               "steps": e2e_steps, "env_steps_per_step": T,
-               "pcie_gbs_this_rank": {"d2h": d2h * T * e2e_steps / el_local / 1e9, "h2d": h2d * T * e2e_steps / el_local / 1e9},
-               "api": "BatchedDrones.reset + BatchedDrones.rollout_host -> ds_reset + ds_rollout_host (pinned host "
-                      "buffers, H2D/D2H pipelined against the kernel)",
-               "note": "state, observations, rewards, neighbour lists, collision counts and finished flags of "
-                       "every step come back; the velocity columns equal the supplied actions "
-                       "(drone_env.py:238) and are returned as a view of the host action stream"
-                       + ("; z as float32 (what utils.py:305 casts to) and Ni as u8" if args.e2e_compact else "")}
+
+        def e2e_leg(compact):
+            hout = {}
+
+            def e2e_run(total):
+                for ep in range(total):
+                    env.reset(h_start[ep % 2])                       # H2D of the start state + observe
+                    env.rollout_host(actions=h_act[ep % 2], record=RECORD, out=hout, compact=compact)
+
+            e2e_run(2)
+            leg.barrier()
+            t0 = time.perf_counter()
+            e2e_run(e2e_steps)
+            leg.barrier()
+            el_local = time.perf_counter() - t0
+            el = torch.tensor([el_local], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            zb, nib = (4, 1) if compact else (rb, 4)
+            d2h = A * (2 * rb + rb + rb + zc * zb + nib * (K_CLOSEST + 1)) + E * 5
+            h2d = A * 2 * rb
+            return {"value": world * E * n * T * e2e_steps / float(el.item()), "unit": "agent-steps/s",
+                    # per bench step (= one episode of T env-steps)
+                    "h2d_bytes_per_step": h2d * T + A * 2 * 8,
+                    # pos, r, true_r, z, Ni, ncoll, finished; vel (= the action, drone_env.py:238) is returned
+                    # as a view of the host action stream and does not cross PCIe
+                    "d2h_bytes_per_step": d2h * T + E * 4 * 8,
+                    "steps": e2e_steps, "env_steps_per_step": T,
+                    "pcie_gbs_this_rank": {"d2h": d2h * T * e2e_steps / el_local / 1e9,
+                                           "h2d": h2d * T * e2e_steps / el_local / 1e9},
+                    "api": "BatchedDrones.reset + BatchedDrones.rollout_host -> ds_reset + ds_rollout_host (pinned host "
+                           "buffers, H2D/D2H pipelined against the kernel)",
+                    "observations": ("z as float32 (what the reference's actors cast it to, utils.py:305) and Ni as u8 "
+                                     "on the host side (DS_HOST_COMPACT_OBS)") if compact else "z and Ni as the kernel writes them (float64 / int32)",
+                    "note": "state, observations, rewards, neighbour lists, collision counts and finished flags of "
+                            "every step come back; the velocity columns equal the supplied actions "
+                            "(drone_env.py:238) and are returned as a view of the host action stream"}
+
+        e2e = e2e_leg(not args.e2e_full)
+        if not args.e2e_full:
+            e2e_full = e2e_leg(False)
     leg.free()
 
     # BASELINE configs 4 and 5, strong-sharded over the ranks of this run
@@ -522,6 +579,8 @@ def run_ours(args, wl):
         if world > 1:
             dist.destroy_process_group()
         return
+    if isinstance(numa, dict) and "_orig" in numa:          # the CPU baselines use every core of the box
+        os.sched_setaffinity(0, numa.pop("_orig"))
     cpu = cpu_ref = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -543,16 +602,13 @@ def run_ours(args, wl):
                           "two alternating action buffers; no flush"),
                    "log_mode": args.log_mode},
         "roofline": roof, "agg_check": agg_check,
-        "cpu_baseline": cpu, "cpu_baseline_reference": cpu_ref, "e2e": e2e, "gpu_launches": launches,
+        "cpu_baseline": cpu, "cpu_baseline_reference": cpu_ref, "e2e": e2e, "e2e_full_precision_obs": e2e_full,
+        "gpu_launches": launches, "numa_pinning": numa,
         "clocks": clocks, "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def leg_e2e_kwargs(args):
-    return {"compact": True} if args.e2e_compact else {}
 
 
 def main():
@@ -569,7 +625,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config4 / config5 legs")
-    ap.add_argument("--e2e-compact", action="store_true", help="e2e with z as float32 and Ni as u8 on the host side")
+    ap.add_argument("--e2e-full", action="store_true", help="e2e with float64 z / int32 Ni on the host side only")
     ap.add_argument("--ref-kind", default="auto", choices=["auto", "reference", "port"])
     ap.add_argument("--ref-step-seconds", type=float, default=6.0,
                     help="--impl reference: upper bound on the CPU time of one step's sample")

@@ -95,8 +95,10 @@ class BatchedDrones:
         self.Ni = piece(self._block, "Ni"); self.Ni.fill_(-1)
         self.n_collisions, self.finished = piece(self._block, "nc"), piece(self._block, "fin")
         self.internal_t = torch.zeros(E, dtype=torch.int32, device=dev)
-        self.done = torch.zeros(E, dtype=torch.uint8, device=dev)
-        self.agg = torch.zeros((E, 4), dtype=torch.float64, device=dev)
+        # per-episode bookkeeping in ONE allocation: a reset clears it with a single fill
+        self._episode = torch.zeros(E * 32 + E, dtype=torch.uint8, device=dev)
+        self.agg = self._episode[:E * 32].view(torch.float64).view(E, 4)
+        self.done = self._episode[E * 32:]
         self._agg_sum = torch.zeros(5, dtype=torch.float64, device=dev)
 
         # constants -> device (ds_create)
@@ -157,8 +159,7 @@ class BatchedDrones:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ds_reset(self._h, sp.ctypes.data_as(ctypes.c_void_p), ctypes.byref(p),
                                          ctypes.byref(self._io), self._stream()), "ds_reset")
-        self.done.zero_()
-        self.agg.zero_()
+        self._episode.zero_()
 
     def reset_random(self, seed=0, stream=0):
         """drones.reset() with the start drawn on the device (ds_reset_random): distinct lattice
@@ -170,8 +171,7 @@ class BatchedDrones:
         _lib.check(self.lib.ds_reset_random(self._h, ctypes.c_uint64(int(seed)), ctypes.c_uint32(int(stream)),
                                             d0, d1, ctypes.c_double(formation.LATTICE_PITCH), ctypes.byref(p),
                                             ctypes.byref(self._io), self._stream()), "ds_reset_random")
-        self.done.zero_()
-        self.agg.zero_()
+        self._episode.zero_()
 
     def observe(self):
         """rewards() on the current state (drone_env.py:208): refresh z_states/Ni/rewards."""
@@ -615,10 +615,13 @@ class BatchedDrones:
         out["agg"], out["done"] = self.agg, self.done
         return out
 
-    def episode_aggregates(self):
+    def episode_aggregates(self, out=None):
         """Device-side sum over this rank's environments of the per-env episode accumulators
         -> float64 [5] = (sum_t mean_i r, sum_t mean_i true_r, sum_t collisions, steps, #envs):
-        the vector a rank all-reduces (train_problem.py:98-100,118-121)."""
-        _lib.check(self.lib.ds_reduce_aggregates(self._h, _ptr(self.agg), _ptr(self._agg_sum),
+        the vector a rank all-reduces (train_problem.py:98-100,118-121).  out: a caller-owned
+        float64 [5] device tensor (e.g. one of a ring, when the all-reduce runs asynchronously)."""
+        dst = self._agg_sum if out is None else out
+        assert dst.is_cuda and dst.dtype == torch.float64 and dst.numel() == 5
+        _lib.check(self.lib.ds_reduce_aggregates(self._h, _ptr(self.agg), _ptr(dst),
                                                  self._stream()), "ds_reduce_aggregates")
-        return self._agg_sum
+        return dst

@@ -439,7 +439,7 @@ int launch_rollout2(ds_handle *h, const ds::RolloutArgs &ra, cudaStream_t st)
     a.ra = ra;
     a.goal_t2 = h->real_bytes == 8 ? goal_threshold_sq<double>(ra.s.goal_tol) : goal_threshold_sq<float>(ra.s.goal_tol);
     {   // time segments: segment k pays rho chunk-equivalents per chunk in front of it (its prefix pass), so
-        // its own length shrinks accordingly: L_k = L_0 - rho * (L_0 + ... + L_{k-1})
+        // its own length shrinks accordingly: L_k = L_0 - rho * (L_0 + ... + L_{k-1}); a CTA's warps finish together
         const int S = h->ro2_threads / 32, TCw = 32 / h->n;
         const int nchunks = (ra.T + TCw - 1) / TCw;
         const double rho = env_int("DS_RO2_RHO_PERMILLE", 70) / 1000.0;
@@ -455,7 +455,6 @@ int launch_rollout2(ds_handle *h, const ds::RolloutArgs &ra, cudaStream_t st)
         }
         for (int k = S + 1; k <= ds::kRo2MaxSeg; ++k) a.seg_c0[k] = nchunks;
     }
-    if (a.goal_t2 < 0 && !(ra.s.goal_tol >= 0)) a.goal_t2 = -1.0;
     // TMA: 16-byte aligned source, slice blocks a multiple of 16 bytes.  2: one 2-D tile per chunk
     // (tensor map over [T][E * n * 2] Reals); 1: one 1-D bulk copy per slice; 0: per-lane loads.
     const size_t rb = (size_t)h->real_bytes, blk = (size_t)h->n * 2 * rb;
@@ -939,6 +938,19 @@ try {
     a.pos = io->pos; a.vel = io->vel; a.t = io->t; a.fin = io->finished;
     const int threads = 128, warps = threads / 32;         // one warp per environment
     const int blocks = (h->E + warps - 1) / warps;
+    if (h->n <= 32 && h->k == 2 && io->reward && io->true_reward && io->z && io->Ni && io->ncoll &&
+        env_int("DS_RESET_FUSED", 1)) {
+        // draws and the start state's observation in one launch (lane = agent)
+        ds::ResetObsArgs ro;
+        ro.r = a;
+        if (int rc = fill_step_args(h, p, io, nullptr, false, &ro.s)) return rc;
+        const size_t smem2 = ds::CtaSmem<double>::align16(sizeof(int) * (size_t)h->n * warps) +
+                             (size_t)warps * h->n * 2 * h->real_bytes;
+        if (h->real_bytes == 8) ds::reset_observe_kernel<double><<<blocks, threads, smem2, st>>>(ro);
+        else ds::reset_observe_kernel<float><<<blocks, threads, smem2, st>>>(ro);
+        DS_CUDA(cudaGetLastError());
+        return DS_OK;
+    }
     const size_t smem = sizeof(int) * (size_t)h->n * warps;
     if (h->real_bytes == 8) ds::reset_random_kernel<double><<<blocks, threads, smem, st>>>(a);
     else ds::reset_random_kernel<float><<<blocks, threads, smem, st>>>(a);

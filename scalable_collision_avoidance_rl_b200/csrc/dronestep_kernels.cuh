@@ -1703,6 +1703,81 @@ __global__ void __launch_bounds__(128) reset_random_kernel(const ResetArgs a)
     }
 }
 
+// The same reset with the observation of the start state (init_agents' rewards() call, drone_env.py:
+// 208-210) in the SAME launch, for n <= 32 and k = 2: after the draws the lanes of the environment's
+// warp are its agents and evaluate their rows with the step kernel's code (eval_row / write_obs) on
+// the positions the warp has just written to shared memory.  Bit-identical to reset_random_kernel
+// followed by step_kernel(do_integrate = 0); one launch less per episode.
+struct ResetObsArgs {
+    ResetArgs r;
+    StepArgs s;
+};
+
+template <typename Real>
+__global__ void __launch_bounds__(128) reset_observe_kernel(const ResetObsArgs ra)
+{
+    using V2 = typename vec2_of<Real>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ResetArgs &a = ra.r;
+    const StepArgs &sa = ra.s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, n = a.n;
+    int *picks = reinterpret_cast<int *>(smem_raw) + (size_t)w * n;
+    V2 *spos = reinterpret_cast<V2 *>(smem_raw + CtaSmem<Real>::align16(sizeof(int) * (size_t)n * (blockDim.x >> 5))) + (size_t)w * n;
+    const int e = blockIdx.x * (blockDim.x >> 5) + w;
+    if (e >= a.E) return;                                  // whole warps leave together
+    const unsigned L = (unsigned)a.d0 * (unsigned)a.d1;
+    const unsigned thresh = (0u - L) % L;
+    unsigned rnd[4];
+    unsigned block = 0;
+    int have = 0;
+    V2 *pos = reinterpret_cast<V2 *>(a.pos) + (size_t)e * n;
+    V2 *vel = reinterpret_cast<V2 *>(a.vel) + (size_t)e * n;
+    for (int i = 0; i < n;) {
+        if (have == 0) { philox4x32_10((unsigned)e, block++, a.stream, 0u, a.seed_lo, a.seed_hi, rnd); have = 4; }
+        const unsigned long long m = (unsigned long long)rnd[4 - have] * L;
+        --have;
+        if ((unsigned)m < thresh) continue;
+        const int node = (int)(m >> 32);
+        bool dup = false;
+        for (int q = lane; q < i; q += 32) dup |= (picks[q] == node);
+        if (__any_sync(0xffffffffu, dup)) continue;
+        if (lane == 0) {
+            picks[i] = node;
+            V2 pv, zv;
+            pv.x = (Real)mul_rn((double)(node / a.d1), a.pitch);
+            pv.y = (Real)mul_rn((double)(node % a.d1), a.pitch);
+            zv.x = 0; zv.y = 0;
+            pos[i] = pv; vel[i] = zv; spos[i] = pv;
+        }
+        __syncwarp();
+        ++i;
+    }
+    if (lane == 0) {
+        if (a.t) a.t[e] = 0;
+        if (a.fin) a.fin[e] = 0;
+    }
+    // ---- rewards() on the start state: lane = agent
+    const ParamsR<Real> P(sa);
+    int nc = 0;
+    if (lane < n) {
+        const int i = lane;
+        const AgentConst<Real> c = load_agent_const<Real>(sa.c, i);
+        const V2 p = spos[i];
+        RowResult<Real, 2> o;
+        eval_row<Real, 2>(o, n, i, p.x, p.y, c, spos, reinterpret_cast<const Real *>(sa.c.delta),
+                          reinterpret_cast<const Real *>(sa.c.radius), P, sa.c.logtab);
+        const size_t g = (size_t)e * n + i;
+        reinterpret_cast<Real *>(sa.r)[g] = o.r;
+        reinterpret_cast<Real *>(sa.tr)[g] = o.tr;
+        // zero velocities: the 5-column observation reads them from the frame's velocity array
+        write_obs<Real, 2>(o, i, p.x, p.y, c, spos, reinterpret_cast<const V2 *>(a.vel) + (size_t)e * n,
+                           reinterpret_cast<const Real *>(sa.c.radius), P, reinterpret_cast<Real *>(sa.z), sa.Ni, g);
+        nc = o.ncoll;
+    }
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    if (lane == 0) sa.ncoll[e] = nc;                       // :284
+}
+
 // Deterministic sum over environments of agg[E][4] -> out[0..3]; out[4] = E.
 __global__ void __launch_bounds__(1024) reduce_agg_kernel(const double *__restrict__ agg, int E,
                                                           double *__restrict__ out)

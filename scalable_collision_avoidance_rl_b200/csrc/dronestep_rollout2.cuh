@@ -57,7 +57,11 @@ constexpr int kRo2Stages = 2;       // action ring depth (chunks): chunk c + 1 i
 constexpr int kRo2Threads = 256;    // up to 8 warps = 8 time segments of one environment per CTA
 constexpr int kRo2MaxSeg = 8;
 #ifndef DS_RO2_MINCTAS
-#define DS_RO2_MINCTAS 3            // 24 warps per SM: 80 registers per thread
+#define DS_RO2_MINCTAS 3            // launch bound for 256-thread CTAs
+#endif
+#ifndef DS_RO2_MAXNREG
+#define DS_RO2_MAXNREG 80           // 6 CTAs of 4 warps per SM.  Measured: 72 registers + the log table out of shared
+                                    // memory = 7 CTAs (28 warps) per SM, 3 % slower
 #endif
 
 __host__ __device__ inline size_t ro2_align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -75,16 +79,16 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     static constexpr int GR = LW / (N - 1);                                       // rows per group (overflowing frames)
     static constexpr int ASTR = (int)(((RW * sizeof(V2) + 127) / 128) * 128 / sizeof(V2));   // stage stride: 128-byte aligned (TMA)
     V2 act[kRo2Stages][ASTR]; // action ring: [slice][agent] of a chunk, as in global memory
-    V2 pos[32];               // positions of the chunk's rows (row = lane)
+    V2 pos[RW];               // positions of the chunk's rows (row = lane)
     V2 pend[N];               // agent's position after the previous chunk
-    V2 acc[32];               // running episode sums (r, true_r) of the lane's rows
-    int sumc[32];             // running collision count of the slice's frames (lanes with i == 0)
+    V2 acc[RW];               // running episode sums (r, true_r) of the lane's rows
+    int sumc[TCW];            // running collision count of each slice's frames
     V2 res[LW];               // (d, log term) per ordered near pair, row-contiguous, ascending j
     float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
     uint2 rowinfo[TABLE ? 1 : 32];   // (near mask, first result slot) of each row (segment layout only)
     unsigned ent[LU];         // unordered near pairs
     unsigned umask[32];       // near AND not clipped (pair lanes clear the rare clipped-near bits)
-    int cnt[32];              // collision count per frame (slice)
+    int cnt[TCW + 1];         // collision count per frame (slice); [TCW]: the call's record mask
     unsigned long long mbar[kRo2Stages];
 };
 
@@ -264,11 +268,11 @@ template <typename Real, int N> struct alignas(128) Ro2Cta {
     V2 cF[N];                          // end points
     double part[kRo2MaxSeg][4];        // per-segment episode sums: r, true_r, collisions, steps
     int seg_fin[kRo2MaxSeg];           // the episode ended inside this segment
-    LogTabEntry logtab[sizeof(Real) == 8 ? kLogTabSize : 1];
+    LogTabEntry logtab[sizeof(Real) == 8 ? kLogTabSize : 1];   // (read through L1 from global memory instead: 3.5 % slower)
 };
 
 template <typename Real, int N, int K>
-__global__ void __launch_bounds__(kRo2Threads, DS_RO2_MINCTAS)
+__global__ void __maxnreg__(DS_RO2_MAXNREG)
 rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
 {
     using V2 = typename vec2_of<Real>::type;
@@ -298,7 +302,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         for (int st = 0; st < kRo2Stages; ++st) ro2_mbar_init(&W.mbar[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    W.cnt[lane] = 0;
+    if (lane <= TCW) W.cnt[lane] = 0;
     __syncthreads();
 
     const int s = lane / N, i = lane - s * N;                    // slice in the chunk, agent
@@ -348,6 +352,9 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     // ---- prefix: the state at the start of this warp's segment.  Only the integrator runs over the
     // steps in front of it (two dependent fp64 operations per step; actions fetched eight chunks
     // ahead), with the episode-end test of the main loop: a segment behind the end does nothing.
+    // (Measured alternative: warp 0 alone integrates once and hands every segment its start state
+    // through shared memory and one mbarrier per boundary -- half the prefix instructions, but the
+    // other warps idle until the single-warp pass reaches their boundary: 3 % slower.)
     int tstar = 0x7fffffff;                                     // first step at which every agent is at its goal
     {
         V2 pend{};                                              // agent i's position after the previous chunk
@@ -399,8 +406,8 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     }
         if (lane < N) W.pend[lane] = pend;
         V2 z2; z2.x = 0; z2.y = 0;
-        W.acc[lane] = z2;
-        W.sumc[lane] = 0;
+        if (rowlane) W.acc[lane] = z2;
+        if (lane < TCW) W.sumc[lane] = 0;
         if constexpr (WS::TABLE) {                              // the rows' own slots of the result table: the fold's neutral element
             V2 nv; nv.x = (Real)A.ds; nv.y = 0;
             if (rowlane) W.res[lane * N + i] = nv;
@@ -412,8 +419,8 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     const bool dead = !alive0 || T <= 0 || c0 >= nchunks || tfin_pre < ta;
     int steps = 0;
     if (lane == 0)
-        W.cnt[31] = (int)((ra.pos_tr ? 1u : 0u) | (ra.vel_tr ? 2u : 0u) | (ra.r_tr ? 4u : 0u) | (ra.tr_tr ? 8u : 0u) |
-                          (ra.z_tr ? 16u : 0u) | (ra.ncoll_tr ? 32u : 0u) | (ra.fin_tr ? 64u : 0u));   // record mask (slot 31 is never a frame count: TCW <= 32 only for N = 1)
+        W.cnt[TCW] = (int)((ra.pos_tr ? 1u : 0u) | (ra.vel_tr ? 2u : 0u) | (ra.r_tr ? 4u : 0u) | (ra.tr_tr ? 8u : 0u) |
+                          (ra.z_tr ? 16u : 0u) | (ra.ncoll_tr ? 32u : 0u) | (ra.fin_tr ? 64u : 0u));   // record mask
 
     // ---- action staging.  TMA: lane 0 brings chunk c's [TCW][N][2] block into ring stage (c - c0) % 3
     // (one 2-D tile, or one 1-D bulk copy per slice); lane-load form: every row lane holds the action
@@ -476,7 +483,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             const bool okf = fabs(pm.x) < (Real)1024 && fabs(pm.y) < (Real)1024;   // false for NaN / inf too
             fx = okf ? (float)pm.x : __int_as_float(0x7fc00000);
             fy = okf ? (float)pm.y : __int_as_float(0x7fc00000);
-            W.pos[lane] = pm;
+            if (rowlane) W.pos[lane] = pm;
         }
         if (rowlane) {
             float *pfa = reinterpret_cast<float *>(&W.posf[s * HP + (i >> 1)]) + (i & 1);
@@ -715,7 +722,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         nc = W.cnt[rowlane ? s : 0];
         if (in_chunk) {
             const unsigned fe = (unsigned)(t0 + s) * (unsigned)E + (unsigned)e;
-            const unsigned recmask = (unsigned)W.cnt[31];
+            const unsigned recmask = (unsigned)W.cnt[TCW];
             if (s < ne) {
                 ui = uact[lane];
                 if (recmask & 1u) reinterpret_cast<V2 *>(ra.pos_tr)[at] = W.pos[lane];
@@ -734,7 +741,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                     W.acc[lane] = acc;
                 }
                 if (i == 0) {
-                    W.sumc[lane] += nc;
+                    W.sumc[s] += nc;
                     if (recmask & 32u) ra.ncoll_tr[fe] = nc;
                     if (recmask & 64u) ra.fin_tr[fe] = (env_fin && s == ne - 1) ? 1 : 0;
                 }
@@ -780,7 +787,8 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     }
     // ---- episode sums (train_problem.py:98-100): sum over the call of mean_i r, mean_i true_r, the
     // collision counts and the steps; rows of a segment reduced over the warp, segments in time order
-    double sr = (double)W.acc[lane].x, stt = (double)W.acc[lane].y, sc = (double)W.sumc[lane];
+    double sr = rowlane ? (double)W.acc[lane].x : 0.0, stt = rowlane ? (double)W.acc[lane].y : 0.0;
+    double sc = lane < TCW ? (double)W.sumc[lane] : 0.0;
 #pragma unroll
     for (int w = 16; w > 0; w >>= 1) {
         sr += __shfl_xor_sync(0xffffffffu, sr, w);

@@ -27,13 +27,18 @@ def shard_envs(n_envs_total: int, rank: int, world_size: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allreduce_episode_aggregates(agg5: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place SUM all-reduce of the float64 [5] episode aggregate vector."""
+def allreduce_episode_aggregates(agg5: torch.Tensor, group=None, async_op: bool = False):
+    """In-place SUM all-reduce of the float64 [5] episode aggregate vector.  async_op=True: the
+    collective runs on NCCL's own stream behind the rollout that produced agg5 and the caller's
+    stream does NOT wait for it (the next episode does not depend on the aggregate); returns the
+    work handle to wait() on before the vector is read or its buffer reused (None when there is
+    nothing to reduce)."""
     if agg5.dtype != torch.float64 or agg5.numel() != len(AGG_FIELDS):
         raise ValueError("expected the float64 [5] vector of BatchedDrones.episode_aggregates()")
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(agg5, op=dist.ReduceOp.SUM, group=group)
-    return agg5
+        work = dist.all_reduce(agg5, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return work if async_op else agg5
+    return None if async_op else agg5
 
 
 def episode_summary(agg5: torch.Tensor) -> dict:

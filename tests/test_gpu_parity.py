@@ -797,6 +797,24 @@ def test_device_reset_matches_restatement(n, E, grid):
     compare_obs(env.z_states.cpu().numpy(), env.Ni.cpu().numpy(), ref.z, ref.Ni, ref.tie, FP64_TOL, "start obs")
 
 
+@pytest.mark.parametrize("n,grid,simplify,dtype", [(10, [5, 5], True, torch.float64), (32, [32, 32], False, torch.float64),
+                                                   (5, [5, 5], True, torch.float32)])
+def test_device_reset_fused_with_observation_equals_two_launches(n, grid, simplify, dtype, monkeypatch):
+    """ds_reset_random draws the start and evaluates its observation in ONE launch (n <= 32, k = 2):
+    every buffer bit-identical to the two-launch form (reset_random_kernel, then ds_observe)."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones
+    E = 300
+    mk = lambda: BatchedDrones(E, n, grid, "O", 2, np.ones(n), simplify, dtype=dtype, seed=1, warn=False)
+    a, b = mk(), mk()
+    a.reset_random(seed=77, stream=5)
+    monkeypatch.setenv("DS_RESET_FUSED", "0")
+    b.reset_random(seed=77, stream=5)
+    torch.cuda.synchronize()
+    for name in ("pos", "vel", "rewards", "true_rewards", "z_states", "Ni", "n_collisions", "finished", "internal_t"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert torch.equal(x, y) or (x.is_floating_point() and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))), name
+
+
 def test_device_reset_statistics():
     """The distribution random.sample gives (drone_env.py:204): every ordered pick is uniform over
     the lattice and the picks of an environment are distinct -- chi-square over 2^17 environments;
