@@ -17,7 +17,10 @@
  *     caller-owned device memory;
  *   - host-pointer entry points (*_host, ds_set_state, ds_get_state) copy
  *     through staging buffers owned by the handle and synchronise the stream
- *     before returning;
+ *     before returning; ds_rollout_host (re)allocates its two device staging
+ *     slots inside the call (after a device synchronise) whenever the chunk
+ *     size or the set of recorded arrays differs from the previous call --
+ *     the one place the library allocates after ds_create;
  *   - a handle is bound to one device and one (n_envs, n_agents, k, precision);
  *     it is not thread-safe; use one handle per rank;
  *   - "Real" is float when ds_config.real_bytes == 4 and double when 8.  The

@@ -29,13 +29,14 @@ done
 # launch list of the bench command (cold-cache, serialised: compare shares)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/launches_config3.csv python bench.py --steps 5 --warmup 3 --no-cpu --no-extra > $OUT/ncu_launches.log 2>&1
+elif [ "$STAGE" = prof ]; then
+# one full capture per call (gpurun brings back at most 64 MiB): $3 = config3 | config4 | hbm
+W=${3:-config3}
+EXTRA=""; [ "$W" = hbm ] && EXTRA="--steps 2"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout2_kernel -s 3 -c 1 \
+    -o $OUT/prof_$W python bench.py --workload $W --steps 3 --warmup 3 --no-cpu --no-e2e --no-extra $EXTRA > $OUT/ncu_full_$W.log 2>&1
+tail -2 $OUT/ncu_full_$W.log
 else
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout2_kernel -s 3 -c 1 \
-    -o $OUT/prof_config3 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-extra > $OUT/ncu_full_config3.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:rollout2_kernel -s 3 -c 1 \
-    -o $OUT/prof_config4 python bench.py --workload config4 --steps 3 --warmup 3 --no-cpu --no-e2e --no-extra > $OUT/ncu_full_config4.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:rollout2_kernel -s 3 -c 1 \
-    -o $OUT/prof_hbm python bench.py --workload hbm --steps 2 --warmup 3 --no-cpu --no-e2e --no-extra > $OUT/ncu_full_hbm.log 2>&1
 # memcheck + racecheck + synccheck over the rollout tests (small cases)
 for tool in memcheck racecheck synccheck; do
 timeout 1200 compute-sanitizer --tool $tool python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "rollout_vs_oracle_and_stepping or dense_and_large or returns_recipe or fused_with_observation" > $OUT/sanitizer_$tool.log 2>&1

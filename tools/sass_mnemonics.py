@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Static evidence, no GPU needed: per-kernel counts of the SASS mnemonics that show which hardware
 paths the shipped libdronestep.so uses (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR =
-tcgen05.commit, UBLKCP = cp.async.bulk, SYNCS = mbarrier, LDGSTS = cp.async, FFMA2 / FADD2 / FMUL2 =
+tcgen05.commit, UTMALDG = cp.async.bulk.tensor (TMA tile load), UBLKCP = cp.async.bulk, SYNCS = mbarrier, LDGSTS = cp.async, FFMA2 / FADD2 / FMUL2 =
 packed f32, DFMA / DADD / DMUL = the fp64 chain, MUFU.RSQ64H / RCP64H = fp64 sqrt / division seeds).
 Usage: python tools/sass_mnemonics.py [substring ...] > profiles/rNN/..._sass_mnemonics.txt"""
 import collections, os, re, subprocess, sys
 
-KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "SYNCS", "LDGSTS", "FFMA2", "FADD2", "FMUL2", "DFMA", "DADD", "DMUL",
+KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "FFMA2", "FADD2", "FMUL2", "DFMA", "DADD", "DMUL",
         "MUFU.RSQ64H", "MUFU.RCP64H", "BAR.SYNC", "STG.E.128", "STG.E.64", "LDS.128", "STS.128", "ATOMS", "REDUX",
         "SHFL", "VOTE", "LDG.E"]
 DEFAULT = ("rollout_kernel<double, 2, 256, 1>", "rollout_kernel<float, 2, 256, 1>", "policy_kernel<double, 6>",
