@@ -315,11 +315,12 @@ class GpuLeg:
     region touches (action streams, trajectory buffers, the library's launch plan) exists before
     the first event: the warm-up runs launches of the IDENTICAL shape."""
 
-    def __init__(self, wl, E_local, dtype_name, dev, rank, world, log_mode=0, T=None, seed=1234):
+    def __init__(self, wl, E_local, dtype_name, dev, rank, world, log_mode=0, T=None, seed=1234, strong=False):
         import torch
         from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
         self.torch = torch
         self.wl, self.E, self.n, self.rank, self.world, self.dev = wl, E_local, wl["n"], rank, world, dev
+        self.strong = strong                                 # E_local is this rank's shard of wl["E"]
         self.T = T or wl.get("episode", EPISODE)
         self.dtype = torch.float64 if dtype_name == "f64" else torch.float32
         self.rb = 8 if dtype_name == "f64" else 4
@@ -339,15 +340,14 @@ class GpuLeg:
         self.out = {}
         # ds_reset_random: draws + start observation in one launch for n <= 32, k = 2 (else two launches)
         self.reset_launches = 1 if (n <= 32 and K_CLOSEST == 2 and os.environ.get("DS_RESET_FUSED", "1") != "0") else 2
-        self.agg_ring = [torch.zeros(5, dtype=torch.float64, device=dev) for _ in range(4)]
-        self.agg_work = [None] * 4
+        self.agg_rows = torch.zeros((1024, 5), dtype=torch.float64, device=dev)   # one row per episode of a run
         self.seed = seed + rank
         self.ep = 0
         self.launches = 0
         self.stream = torch.cuda.current_stream(dev)
         self.events = []
 
-    def episode(self, timed, allreduce=True):
+    def episode(self, timed):
         """env.reset() on the device (drone_env.py:98-102,193-210: fresh distinct lattice nodes per
         environment, zero velocity, t = 0, initial observation), one fused rollout of the episode,
         device-side reduction of the episode aggregates (+ the all-reduce)."""
@@ -361,29 +361,27 @@ class GpuLeg:
         if timed:
             e1.record(self.stream)
             self.events.append((e0, e1))
-        # device-side reduce into one of a ring of result vectors, no host sync; the all-reduce of the
-        # 5 doubles runs on NCCL's stream behind it: the next episode does not wait for it
-        slot = self.ep % len(self.agg_ring)
-        if self.agg_work[slot] is not None:
-            self.agg_work[slot].wait()
-            self.agg_work[slot] = None
-        agg = self.env.episode_aggregates(out=self.agg_ring[slot]); self.launches += 1
-        if self.world > 1 and allreduce:
-            from scalable_collision_avoidance_rl_b200 import dist as dsdist
-            self.agg_work[slot] = dsdist.allreduce_episode_aggregates(agg, async_op=True)
+        # device-side reduce of this episode's aggregates into its row of the run's table, no host
+        # sync; the rows are all-reduced together once, at the end of the timed episodes (run())
+        row = self.agg_rows[self.ep % self.agg_rows.shape[0]]
+        agg = self.env.episode_aggregates(out=row); self.launches += 1
         self.ep += 1
         return agg
 
-    def drain(self):
-        """The launch stream waits for every all-reduce still in flight (inside the timed region: the
-        last episodes' aggregates belong to the K steps)."""
-        for q, w in enumerate(self.agg_work):
-            if w is not None:
-                w.wait()
-                self.agg_work[q] = None
+    def allreduce_rows(self, first_ep, count):
+        """ONE all-reduce (NCCL) of the per-episode aggregate rows of `count` episodes: the single
+        exchange of the sharded path ("a single all-reduce of episode returns at the end"), enqueued
+        behind the last rollout, inside the timed region."""
+        if self.world > 1 and count > 0:
+            import torch.distributed as dist
+            R = self.agg_rows.shape[0]
+            lo = first_ep % R
+            if lo + count <= R:
+                dist.all_reduce(self.agg_rows[lo:lo + count], op=dist.ReduceOp.SUM)
+            else:                                            # (wrapped: more than 1024 episodes in flight)
+                dist.all_reduce(self.agg_rows, op=dist.ReduceOp.SUM)
 
     def barrier(self):
-        self.drain()
         if self.world > 1:
             import torch.distributed as dist
             dist.barrier()
@@ -402,10 +400,12 @@ class GpuLeg:
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
         self.barrier()
         g0.record(self.stream)
+        ep0 = self.ep
         for _ in range(K):
             self.episode(True)
-        self.drain()
+        self.allreduce_rows(ep0, K)
         g1.record(self.stream)
+        self.timed_rows = (ep0, K)
         self.barrier()
         ms = g0.elapsed_time(g1)
         tms = torch.tensor([ms], dtype=torch.float64, device=self.dev)
@@ -421,10 +421,16 @@ class GpuLeg:
         of a random walk reaches its goal formation)."""
         torch = self.torch
         self.barrier()
-        agg = self.episode(False, allreduce=False).clone()
+        # the rows the timed run reduced: every episode must account for every environment-step of every rank
+        ep0, K = getattr(self, "timed_rows", (0, 0))
+        R = self.agg_rows.shape[0]
+        rows = self.agg_rows[[(ep0 + q) % R for q in range(min(K, R))]].cpu().numpy() if K else np.zeros((0, 5))
+        tot_envs = float(self.wl["E"]) if self.strong else float(self.world * self.E)
+        timed_ok = bool(len(rows) == 0 or (np.abs(rows[:, 3] - tot_envs * self.T) < 0.5).all() and (rows[:, 4] == tot_envs).all())
+        agg = self.episode(False).clone()
         want_steps = float(self.E * self.T)
         ok_local = abs(float(agg[3].item()) - want_steps) < 0.5 and float(agg[4].item()) == float(self.E)
-        res = {"steps_per_rank_ok": bool(ok_local)}
+        res = {"steps_per_rank_ok": bool(ok_local), "timed_episodes_reduced_ok": timed_ok}
         if self.world > 1:
             import torch.distributed as dist
             from scalable_collision_avoidance_rl_b200 import dist as dsdist
@@ -556,7 +562,7 @@ def run_ours(args, wl):
         for name in ("config4", "config5"):
             w2 = WORKLOADS[name]
             lo, hi = dsdist.shard_envs(w2["E"], rank, world)
-            l2 = GpuLeg(w2, hi - lo, args.dtype, dev, rank, world, args.log_mode, EPISODE, seed=4321)
+            l2 = GpuLeg(w2, hi - lo, args.dtype, dev, rank, world, args.log_mode, EPISODE, seed=4321, strong=True)
             K2 = 10
             ms2, kms2 = l2.run(K2, 3)
             chk = l2.agg_check()
