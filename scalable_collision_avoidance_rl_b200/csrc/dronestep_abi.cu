@@ -705,7 +705,29 @@ try {
     DeviceGuard guard(h->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const Geom gm{h->step_blocks, h->step_threads, h->step_smem};
-    return launch_rollout_control(h, ra, gm, st);
+    // One launch for the whole closed-loop episode (default).  DS_CTRL_FUSED=0 issues T launches of the
+    // same kernel's one-step form instead -- same semantics, kept for comparison: measured on B200 at
+    // the config-3 batch (profiles/r02/final_bench_closed_loop.json) the single launch executes
+    // 2.4e9 agent-steps/s, T one-step launches 1.4e9 (most environments finish after ~90 steps, the
+    // remaining launches find nothing to do).  Round 1's "3.4e9 with one launch per step" counted
+    // ds_step_control launches, which keep stepping environments whose episode has ended.
+    if (env_int("DS_CTRL_FUSED", 1) || ro->T == 1) return launch_rollout_control(h, ra, gm, st);
+    const size_t E = (size_t)h->E, EN = E * h->n, rb = (size_t)h->real_bytes;
+    const size_t zc = (size_t)(h->k + 1) * (h->simplify ? 2 : 5);
+    auto off = [](void *base, size_t bytes) -> void * { return base ? (void *)((char *)base + bytes) : nullptr; };
+    ra.T = 1;
+    for (int t = 0; t < ro->T; ++t) {
+        ra.pos_tr = off(ro->pos_tr, (size_t)t * EN * 2 * rb);
+        ra.vel_tr = off(ro->vel_tr, (size_t)t * EN * 2 * rb);
+        ra.r_tr = off(ro->reward_tr, (size_t)t * EN * rb);
+        ra.tr_tr = off(ro->true_reward_tr, (size_t)t * EN * rb);
+        ra.z_tr = off(ro->z_tr, (size_t)t * EN * zc * rb);
+        ra.Ni_tr = (int *)off(ro->Ni_tr, (size_t)t * EN * (h->k + 1) * sizeof(int32_t));
+        ra.ncoll_tr = (int *)off(ro->ncoll_tr, (size_t)t * E * sizeof(int32_t));
+        ra.fin_tr = (uint8_t *)off(ro->finished_tr, (size_t)t * E);
+        if (int rc = launch_rollout_control(h, ra, gm, st)) return rc;
+    }
+    return DS_OK;
 } catch (const std::exception &ex) {   // nothing C++ crosses the C boundary
     return fail(DS_ERR_INTERNAL, std::string("ds_rollout_control: host exception: ") + ex.what());
 } catch (...) {
