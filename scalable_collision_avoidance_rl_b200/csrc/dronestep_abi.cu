@@ -87,7 +87,7 @@ int env_int(const char *name, int dflt);
 // same radius, d_safety and Delta (any scalar-delta configuration of the reference), 0 <= Delta,
 // 0 < d_safety, the pass-1 threshold is finite, k = 2, the 2-column observation, and n is one of
 // the instantiated agent counts.  DS_RO2=0 forces rollout_kernel (A/B runs).
-#define DS_RO2_NS(X) X(5) X(10) X(32)
+#define DS_RO2_NS(X) X(4) X(5) X(8) X(10) X(16) X(20) X(32)
 template <typename Real, int N> size_t ro2_warp_bytes() { return sizeof(ds::Ro2Warp<Real, N>); }
 template <typename Real, int N> size_t ro2_cta_bytes() { return ds::ro2_align16(sizeof(ds::Ro2Cta<Real, N>)); }
 template <typename Real>

@@ -356,6 +356,56 @@ def test_float32_free_running_episode_drift(n, grid, delta, box):
         assert nc64[live].sum() > 0
 
 
+@pytest.mark.parametrize("n,grid,delta,box", [(4, [5, 5], 1.0, None), (5, [5, 5], 1.0, 1.2), (8, [5, 5], 0.8, None),
+                                              (10, [5, 5], 1.0, 1.5), (16, [12, 12], 1.5, None), (20, [12, 12], 1.0, 4.0),
+                                              (32, [32, 32], 2.5, None), (32, [32, 32], 2.5, 6.0), (10, [5, 5], None, None)])
+def test_rollout2_every_instantiation_equals_general_kernel(n, grid, delta, box, monkeypatch):
+    """Every agent count the warp-per-segment kernel is instantiated for, sparse and dense (the dense
+    cases overflow the pair list of the segment layout / fill the pair table), delta=None (every agent
+    inside every Delta disk), T not a multiple of the chunk, environments that start late in their
+    episode and finish inside the call, a second call continuing the first: bit-identical to the
+    general rollout_kernel (itself pinned to the oracle and the reference's vectors) in EVERY output."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    E, T = 67, 53
+    rng = np.random.default_rng(n)
+    deltas = None if delta is None else np.ones(n) * delta
+    new = BatchedDrones(E, n, grid, "O", 2, deltas, True, seed=3, warn=False)
+    monkeypatch.setenv("DS_RO2", "0")
+    old = BatchedDrones(E, n, grid, "O", 2, deltas, True, seed=3, warn=False)
+    monkeypatch.delenv("DS_RO2")
+    st, _ = new.get_state()
+    if box is not None:
+        st[:, :, 0:2] = rng.uniform(1.0, 1.0 + box, (E, n, 2))
+        st[0, 1, 0:2] = st[0, 0, 0:2]                              # coincident agents
+    tt = rng.integers(0, 200, E).astype(np.int32)
+    tt[:8] = 199 - rng.integers(0, T, 8)                           # these hit the time limit inside the call
+    act = torch.as_tensor(formation.unit_action_table(16)[rng.integers(0, 16, (2 * T, E, n))], device=new.device)
+    rec = ("pos", "vel", "reward", "true_reward", "obs", "ncoll", "finished")
+    outs = []
+    for env in (new, old):
+        env.set_state(st, tt); env.observe()
+        a = {k: v.clone() for k, v in env.rollout(actions=act[:T], record=rec).items()}
+        b = {k: v.clone() for k, v in env.rollout(actions=act[T:], record=rec).items()}     # continues: done / t / agg carry over
+        live = {name: getattr(env, name).clone() for name in ("pos", "vel", "rewards", "true_rewards", "z_states", "Ni",
+                                                               "n_collisions", "finished", "internal_t", "done")}
+        outs.append((a, b, live, env.agg.clone()))
+    torch.cuda.synchronize()
+    (a1, b1, l1, g1), (a0, b0, l0, g0) = outs
+    fin = a0["finished"].cpu().numpy()
+    assert (fin == 1).any() and (fin == 2).any()
+    for x, y, what in ((a1, a0, "first call"), (b1, b0, "second call")):
+        ex = (y["finished"] != 2)                                  # [T,E]: executed steps
+        for key in ("pos", "vel", "reward", "true_reward", "z", "Ni"):
+            xs, ys = x[key][ex], y[key][ex]
+            assert torch.equal(torch.nan_to_num(xs.double()), torch.nan_to_num(ys.double())), f"{what}: {key}"
+        assert torch.equal(x["ncoll"][ex], y["ncoll"][ex]) and torch.equal(x["finished"], y["finished"]), what
+    for name in l0:
+        assert torch.equal(torch.nan_to_num(l1[name].double()), torch.nan_to_num(l0[name].double())), f"live {name}"
+    assert torch.allclose(g1, g0, rtol=0, atol=1e-9)               # episode sums: same terms, different reduction order
+    if box is not None:
+        assert (a0["ncoll"] > 0).any()
+
+
 def test_log_mode_rcp_within_stated_difference():
     """DS_LOG_RCP (log(d_safety / d) as -log(d * (1 / d_safety)), no division): rewards within 1e-13 of
     the DS_LOG_DIV path (stated: <= 3.4e-16 per barrier term, times b = 0.01, times <= n terms), every
