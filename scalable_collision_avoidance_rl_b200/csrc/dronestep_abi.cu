@@ -119,6 +119,10 @@ void plan_rollout2(ds_handle *h, const Real *dsv, const Real *dl, const Real *rd
         a.thr2f = f;
     }
     a.delta_eff = clipcnt[0] != 0 ? (double)INFINITY : (double)dl[0];
+    {   // an agent's own entry: min(d_safety, ((0 - l) - l)) in Real arithmetic (drone_env.py:318-325)
+        const Real raw_ii = ((Real)0 - rd[0]) - rd[0];
+        a.d_ii = (double)((dsv[0] < raw_ii) ? dsv[0] : raw_ii);
+    }
     // one CTA per environment; its warps are the time segments of a call
     // enough warps to cover the SMs' resident slots (~24 per SM) about four times: short CTA lifetimes
     // keep the drain at the end of the launch small; more segments only add prefix work

@@ -34,6 +34,7 @@
 // The arithmetic (operation order of eval_pair / row_end / write_obs) is that of
 // dronestep_kernels.cuh, so this kernel, rollout_kernel and step_kernel agree bit for bit.
 #pragma once
+#include <type_traits>
 #include <cuda.h>      // CUtensorMap (type only; the encoder is resolved at run time by the host side)
 #include "dronestep_kernels.cuh"
 
@@ -46,6 +47,7 @@ struct Ro2Args {
     // uniform per-agent constants
     double ds, delta, radius, log_ds, inv_ds;
     double delta_eff;       // Delta, or +inf when d_safety <= Delta (every agent is inside every Delta disk)
+    double d_ii;            // the clipped 'distance' of an agent to itself: min(d_safety, -2 radius) (:318-325)
     double goal_t2;         // largest x with sqrt_rn(x) <= goal_tol: the goal test without the square root
     float thr2f;            // pass-1 threshold of the packed-f32 filter (squared, with margin)
     int act_mode;           // action staging: 0 lane loads, 1 cp.async.bulk per slice, 2 one 2-D TMA tile per chunk
@@ -86,7 +88,7 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     V2 res[LW];               // (d, log term) per ordered near pair, row-contiguous, ascending j
     float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
     uint2 rowinfo[TABLE ? 1 : 32];   // (near mask, first result slot) of each row (segment layout only)
-    unsigned ent[LU];         // unordered near pairs
+    unsigned ent[LU + 1];     // unordered near pairs; [LU]: where lanes that ran out of pairs store
     unsigned umask[32];       // near AND not clipped (pair lanes clear the rare clipped-near bits)
     int cnt[TCW + 1];         // collision count per frame (slice); [TCW]: the call's record mask
     unsigned long long mbar[kRo2Stages];
@@ -253,12 +255,20 @@ __device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::typ
 // -np.nan_to_num(v) (drone_env.py:287-288); the rewards are finite unless a position is not
 DS_HD double ro2_neg_nan_to_num(double v)
 {
+#if defined(__CUDA_ARCH__)
+    if ((__double2hiint(v) & 0x7ff00000) == 0x7ff00000) v = nan_to_num(v);      // inf or NaN: exponent all ones
+#else
     if (!(fabs(v) <= 1.7976931348623157e308)) v = nan_to_num(v);
+#endif
     return -v;
 }
 DS_HD float ro2_neg_nan_to_num(float v)
 {
+#if defined(__CUDA_ARCH__)
+    if ((__float_as_int(v) & 0x7f800000) == 0x7f800000) v = nan_to_num(v);
+#else
     if (!(fabsf(v) <= 3.4028234663852886e38f)) v = nan_to_num(v);
+#endif
     return -v;
 }
 
@@ -506,13 +516,13 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             constexpr int NB = (N <= 2) ? 1 : (N <= 4) ? 2 : (N <= 8) ? 3 : (N <= 16) ? 4 : 5;
             const int cUl = __popc(mU);
             const unsigned ltmask = (1u << lane) - 1u;
-            int baseU = 0, totU = 0;
+            int baseU = 0;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
                 const unsigned bal = __ballot_sync(0xffffffffu, (cUl >> b) & 1);
                 baseU += __popc(bal & ltmask) << b;
-                totU += __popc(bal) << b;
             }
+            const int totU = (int)__reduce_add_sync(0xffffffffu, (unsigned)cUl);
             {
                 W.umask[lane] = m;
                 unsigned *ep = W.ent + baseU;
@@ -520,10 +530,10 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 const unsigned ew = (unsigned)lane | ((unsigned)i << 5);
                 const int iters = __reduce_max_sync(0xffffffffu, cUl);
 #pragma unroll 1
-                for (int it = 0; it < iters; ++it) {             // straight-line body: lanes out of pairs store nothing
+                for (int it = 0; it < iters; ++it) {             // straight-line body: lanes out of pairs store to the spare slot
                     const bool on = mm != 0;
                     const unsigned j = (unsigned)(__ffs((int)mm) - 1);
-                    if (on) *ep = ew | (j << 10);
+                    *(on ? ep : W.ent + WS::LU) = ew | (j << 10);
                     ep += on ? 1 : 0;
                     mm &= mm - 1;
                 }
@@ -665,8 +675,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             for (int q = 0; q < K; ++q) inr += (nj[q] >= 0 && nd[q] <= delta_eff) ? 1 : 0;
             // the row's own entry (:323-325) precedes every partner unless one coincides with the agent
             // (d_ij == d_ii) and has a lower index: merge with the (d, j) rule
-            const Real raw_ii = sub_rn(sub_rn((Real)0, rad), rad);
-            const Real d_ii = (ds < raw_ii) ? ds : raw_ii;
+            const Real d_ii = (Real)A.d_ii;
             if (nj[0] >= 0 && nd[0] <= d_ii) {                              // coincident agents only
                 int pself = 0;
 #pragma unroll
@@ -725,26 +734,31 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             const unsigned recmask = (unsigned)W.cnt[TCW];
             if (s < ne) {
                 ui = uact[lane];
-                if (recmask & 1u) reinterpret_cast<V2 *>(ra.pos_tr)[at] = W.pos[lane];
-                if (recmask & 2u) reinterpret_cast<V2 *>(ra.vel_tr)[at] = ui;        // :238
-                if (recmask & 4u) reinterpret_cast<Real *>(ra.r_tr)[at] = r_i;
-                if (recmask & 8u) reinterpret_cast<Real *>(ra.tr_tr)[at] = tr_i;
-                if (recmask & 16u) {
-                    V2 *zr = reinterpret_cast<V2 *>(ra.z_tr) + (size_t)at * (K + 1);
-                    int *nl = ra.Ni_tr + (size_t)at * (K + 1);
+                // (the call records everything, the usual case: one warp-uniform test instead of seven)
+                auto stores = [&](auto all_tag) {
+                    constexpr bool ALL = decltype(all_tag)::value;
+                    if (ALL || (recmask & 1u)) reinterpret_cast<V2 *>(ra.pos_tr)[at] = W.pos[lane];
+                    if (ALL || (recmask & 2u)) reinterpret_cast<V2 *>(ra.vel_tr)[at] = ui;        // :238
+                    if (ALL || (recmask & 4u)) reinterpret_cast<Real *>(ra.r_tr)[at] = r_i;
+                    if (ALL || (recmask & 8u)) reinterpret_cast<Real *>(ra.tr_tr)[at] = tr_i;
+                    if (ALL || (recmask & 16u)) {
+                        V2 *zr = reinterpret_cast<V2 *>(ra.z_tr) + (size_t)at * (K + 1);
+                        int *nl = ra.Ni_tr + (size_t)at * (K + 1);
 #pragma unroll
-                    for (int kth = 0; kth <= K; ++kth) { zr[kth] = zrow[kth]; nl[kth] = nirow[kth]; }
-                }
+                        for (int kth = 0; kth <= K; ++kth) { zr[kth] = zrow[kth]; nl[kth] = nirow[kth]; }
+                    }
+                    if (i == 0) {
+                        if (ALL || (recmask & 32u)) ra.ncoll_tr[fe] = nc;
+                        if (ALL || (recmask & 64u)) ra.fin_tr[fe] = (env_fin && s == ne - 1) ? 1 : 0;
+                    }
+                };
+                if (recmask == 0x7fu) stores(std::true_type{}); else stores(std::false_type{});
                 {
                     V2 acc = W.acc[lane];
                     acc.x = add_rn(acc.x, r_i); acc.y = add_rn(acc.y, tr_i);
                     W.acc[lane] = acc;
                 }
-                if (i == 0) {
-                    W.sumc[s] += nc;
-                    if (recmask & 32u) ra.ncoll_tr[fe] = nc;
-                    if (recmask & 64u) ra.fin_tr[fe] = (env_fin && s == ne - 1) ? 1 : 0;
-                }
+                if (i == 0) W.sumc[s] += nc;
             } else if (i == 0 && (recmask & 64u)) {
                 ra.fin_tr[fe] = 2;
             }
