@@ -75,8 +75,11 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     // TABLE: results in a dense [row][partner] table and a list with room for every pair of the
     // chunk (small N); otherwise row-contiguous segments and a list of bounded capacity, with the
     // exact group-wise evaluation for frames that overflow it
-    static constexpr bool TABLE = (size_t)RW * N * sizeof(V2) <= 5120;
-    static constexpr int LW = TABLE ? RW * N : ((RW * (N - 1) < 128) ? RW * (N - 1) : 128);         // result slots
+    // (table row stride RS: an odd number of entries, so that the lanes of a quarter / half warp --
+    // one row each, the same partner column -- fall into different banks)
+    static constexpr int RS = N | 1;
+    static constexpr bool TABLE = (size_t)RW * RS * sizeof(V2) <= 5632;
+    static constexpr int LW = TABLE ? RW * RS : ((RW * (N - 1) < 128) ? RW * (N - 1) : 128);        // result slots
     static constexpr int LU = TABLE ? RW * (N - 1) / 2 : ((RW * (N - 1) / 2 < 64) ? RW * (N - 1) / 2 : 64);   // list entries
     static constexpr int GR = LW / (N - 1);                                       // rows per group (overflowing frames)
     static constexpr int ASTR = (int)(((RW * sizeof(V2) + 127) / 128) * 128 / sizeof(V2));   // stage stride: 128-byte aligned (TMA)
@@ -85,7 +88,7 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     V2 pend[N];               // agent's position after the previous chunk
     V2 acc[RW];               // running episode sums (r, true_r) of the lane's rows
     int sumc[TCW];            // running collision count of each slice's frames
-    V2 res[LW];               // (d, log term) per ordered near pair, row-contiguous, ascending j
+    V2 res[LW + 1];           // (d, log term) per ordered near pair, row-contiguous, ascending j; [LW]: (d_safety, 0)
     float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
     uint2 rowinfo[TABLE ? 1 : 32];   // (near mask, first result slot) of each row (segment layout only)
     unsigned ent[LU + 1];     // unordered near pairs; [LU]: where lanes that ran out of pairs store
@@ -232,21 +235,24 @@ __device__ __forceinline__ void ro2_fold_step(Real dx, Real dy, int j, Real delt
     nd[0] = lt[0] ? dx : nd[0];
     nj[0] = lt[0] ? j : nj[0];
 }
-// rp[i] (the row's own slot) holds (d_safety, +0) for the whole call: never a candidate, adds nothing --
-// what a lane that has run out of partners folds.
+// `neutral` holds (d_safety, +0) for the whole call: never a candidate, adds nothing -- what a lane
+// that has run out of partners folds (one address for all of them: a broadcast, no bank conflict).
 template <typename Real, int K>
-__device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp, unsigned mm, int i,
+__device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp,
+                                               const typename vec2_of<Real>::type *__restrict__ neutral, unsigned mm, int i,
                                                Real delta_eff, Real &sum_all, Real &sum_loc, Real (&nd)[K], int (&nj)[K])
 {
     using V2 = typename vec2_of<Real>::type;
     const int iters = (__reduce_max_sync(0xffffffffu, __popc(mm)) + 1) >> 1;
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
-        const int j0 = mm ? __ffs((int)mm) - 1 : i;
+        const int j0 = __ffs((int)mm) - 1;
+        const V2 *p0 = mm ? rp + j0 : neutral;
         mm &= mm - 1;
-        const int j1 = mm ? __ffs((int)mm) - 1 : i;
+        const int j1 = __ffs((int)mm) - 1;
+        const V2 *p1 = mm ? rp + j1 : neutral;
         mm &= mm - 1;
-        const V2 d0 = rp[j0], d1 = rp[j1];
+        const V2 d0 = *p0, d1 = *p1;
         ro2_fold_step<Real, K>(d0.x, d0.y, j0, delta_eff, sum_all, sum_loc, nd, nj);
         ro2_fold_step<Real, K>(d1.x, d1.y, j1, delta_eff, sum_all, sum_loc, nd, nj);
     }
@@ -357,11 +363,14 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             }
         }
     };
-    const int last_lane = (TCW - 1) * N + i;                     // the lane of agent i in the chunk's last slice
 
     // ---- prefix: the state at the start of this warp's segment.  Only the integrator runs over the
-    // steps in front of it (two dependent fp64 operations per step; actions fetched eight chunks
+    // steps in front of it (two dependent fp64 operations per step; actions fetched eight steps
     // ahead), with the episode-end test of the main loop: a segment behind the end does nothing.
+    // (Measured alternatives.  Every lane integrating up to its own slice, as the main loop does:
+    // 19 shared-memory wavefronts per chunk instead of 9.  Lane i < N reading agent i's actions
+    // straight from global memory, step by step: no shared memory, but three times the loads in
+    // flight for the same bytes -- the prefix stalls on them, 5 % slower.)
     // (Measured alternative: warp 0 alone integrates once and hands every segment its start state
     // through shared memory and one mbarrier per boundary -- half the prefix instructions, but the
     // other warps idle until the single-warp pass reaches their boundary: 3 % slower.)
@@ -370,24 +379,28 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         V2 pend{};                                              // agent i's position after the previous chunk
         if (rowlane && alive0) pend = reinterpret_cast<const V2 *>(a.pos)[g];
     if (alive0 && c0 > 0 && c0 < nchunks && tlim >= ta) {
-        V2 pm{};
-        const V2 xF = C.cF[i];
+        // the row lanes fetch the chunks' actions (eight chunks in flight) and pass them through the
+        // action ring; lane i < N takes agent i through the chunk's steps one after the other
+        const bool al = lane < N;
+        const V2 xF = C.cF[al ? lane : 0];
         auto prefix_chunk = [&](const V2 &u, int c, int par2) -> bool {
             V2 *buf = &W.act[par2][0];
             if (rowlane) buf[lane] = u;
             __syncwarp();
-            pm = pend;
-            integrate(buf + i, pm);
-            pend.x = __shfl_sync(0xffffffffu, pm.x, last_lane);
-            pend.y = __shfl_sync(0xffffffffu, pm.y, last_lane);
-            // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
-            const Real gx = sub_rn(xF.x, pm.x), gy = sub_rn(xF.y, pm.y);
-            const bool atg = rowlane && add_rn(mul_rn(gx, gx), mul_rn(gy, gy)) <= (Real)A.goal_t2;
-            const unsigned gbal = __ballot_sync(0xffffffffu, atg);
-            const bool slice_goal = rowlane && i == 0 && (((gbal >> (lane & 31)) & fullN) == fullN);
-            const unsigned sbal = __ballot_sync(0xffffffffu, slice_goal);
-            if (sbal) tstar = c * TCW + (__ffs((int)sbal) - 1) / N;
-            return sbal != 0;
+            unsigned hits = 0;
+#pragma unroll
+            for (int q = 0; q < TCW; ++q) {
+                V2 uq{};
+                if (al) uq = buf[q * N + lane];
+                pend.x = add_rn(pend.x, mul_rn(dt, uq.x));
+                pend.y = add_rn(pend.y, mul_rn(dt, uq.y));
+                // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
+                const Real gx = sub_rn(xF.x, pend.x), gy = sub_rn(xF.y, pend.y);
+                const bool atg = add_rn(mul_rn(gx, gx), mul_rn(gy, gy)) <= (Real)A.goal_t2;
+                hits |= __all_sync(0xffffffffu, atg || !al) ? (1u << q) : 0u;
+            }
+            if (hits) tstar = c * TCW + __ffs((int)hits) - 1;
+            return hits != 0;
         };
         // every slice of a chunk in front of the segment lies inside the call: no bounds to test
         auto run_prefix = [&](auto fetch) {
@@ -418,9 +431,9 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         V2 z2; z2.x = 0; z2.y = 0;
         if (rowlane) W.acc[lane] = z2;
         if (lane < TCW) W.sumc[lane] = 0;
-        if constexpr (WS::TABLE) {                              // the rows' own slots of the result table: the fold's neutral element
+        if constexpr (WS::TABLE) {                              // the fold's neutral element, behind the result table
             V2 nv; nv.x = (Real)A.ds; nv.y = 0;
-            if (rowlane) W.res[lane * N + i] = nv;
+            if (lane == 0) W.res[WS::LW] = nv;
         }
     }
 
@@ -553,8 +566,8 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 ro2_eval_pair<Real>(dv.x, dv.y, coll, pi.x, pi.y, pj.x, pj.y, ds, rad, (Real)A.log_ds, (Real)A.inv_ds,
                                     a.log_mode, (Real)a.zero_eps, (Real)a.sentinel, logtab);
                 if (valid) {
-                    W.res[ri * N + j] = dv;
-                    W.res[rj * N + ii] = dv;
+                    W.res[ri * WS::RS + j] = dv;
+                    W.res[rj * WS::RS + ii] = dv;
                     if (coll) atomicAdd(&W.cnt[(ri - ii) / N], 2);                // both ordered pairs collide (:284,327)
                     if (!(dv.x != ds)) {                                          // near but clipped (inside the f32 margin)
                         atomicAnd(&W.umask[ri], ~(1u << j));
@@ -563,7 +576,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 }
             }
             __syncwarp();
-            ro2_fold_table<Real, K>(W.res + lane * N, m, i, delta_eff, sum_all, sum_loc, nd, nj);
+            ro2_fold_table<Real, K>(W.res + lane * WS::RS, W.res + WS::LW, m, i, delta_eff, sum_all, sum_loc, nd, nj);
         } else {
         const int cFl = __popc(m), cUl = __popc(mU);
         int incl = cUl | (cFl << 16);                            // both counts in one scan
@@ -710,7 +723,8 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             for (int kth = 1; kth <= K; ++kth) {
                 const int j = nj[kth - 1] < 0 ? 0 : nj[kth - 1];
                 const bool in_r = kth <= inr;                                     // :362-368
-                const V2 pj = fpos[rowlane ? j : 0];
+                V2 pj = pm;
+                if (in_r && rowlane) pj = fpos[j];                                // (most rows of a sparse frame: ghosts, no load)
                 zrow[kth].x = in_r ? sub_rn(pj.x, pm.x) : ghx;
                 zrow[kth].y = in_r ? sub_rn(pj.y, pm.y) : ghy;
                 nirow[kth] = in_r ? j : -1;
