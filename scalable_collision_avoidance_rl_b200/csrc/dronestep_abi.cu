@@ -123,9 +123,11 @@ void plan_rollout2(ds_handle *h, const Real *dsv, const Real *dl, const Real *rd
         const Real raw_ii = ((Real)0 - rd[0]) - rd[0];
         a.d_ii = (double)((dsv[0] < raw_ii) ? dsv[0] : raw_ii);
     }
-    // one CTA per environment; its warps are the time segments of a call
-    // enough warps to cover the SMs' resident slots (~24 per SM) about four times: short CTA lifetimes
-    // keep the drain at the end of the launch small; more segments only add prefix work
+    // one CTA per environment; its warps are the time segments of a call.  Enough warps to fill the
+    // SMs' resident slots several times over: short CTA lifetimes keep the partly filled last round of
+    // CTAs small; more segments only add prefix work.  (Measured on B200 at 7 resident 4-warp CTAs per
+    // SM: n = 10, E = 4096: 4 segments 0.383 ms, 2: 0.393, 1: 0.417; n = 32, E = 8192: 2 segments
+    // 1.835 ms, 4: 1.866, 1: 1.861.)
     int segs = 1;
     while (segs < ds::kRo2MaxSeg && (long long)h->E * segs < 4LL * 24 * h->sm_count) segs *= 2;
     segs = env_int("DS_RO2_SEGS", segs);
@@ -446,7 +448,7 @@ int launch_rollout2(ds_handle *h, const ds::RolloutArgs &ra, cudaStream_t st)
         // its own length shrinks accordingly: L_k = L_0 - rho * (L_0 + ... + L_{k-1}); a CTA's warps finish together
         const int S = h->ro2_threads / 32, TCw = 32 / h->n;
         const int nchunks = (ra.T + TCw - 1) / TCw;
-        const double rho = env_int("DS_RO2_RHO_PERMILLE", 70) / 1000.0;
+        const double rho = env_int("DS_RO2_RHO_PERMILLE", 55) / 1000.0;
         double w[ds::kRo2MaxSeg], acc = 0, tot = 0;
         for (int k = 0; k < S; ++k) { w[k] = 1.0 - rho * acc; w[k] = w[k] < 0.1 ? 0.1 : w[k]; acc += w[k]; tot += w[k]; }
         double run = 0;

@@ -62,8 +62,8 @@ constexpr int kRo2MaxSeg = 8;
 #define DS_RO2_MINCTAS 3            // launch bound for 256-thread CTAs
 #endif
 #ifndef DS_RO2_MAXNREG
-#define DS_RO2_MAXNREG 80           // 6 CTAs of 4 warps per SM.  Measured: 72 registers + the log table out of shared
-                                    // memory = 7 CTAs (28 warps) per SM, 3 % slower
+#define DS_RO2_MAXNREG 72           // 7 CTAs of 4 warps per SM (no spills): 4096 environments = 3.95 waves of 7 x 148 CTAs.
+                                    // At 80 registers (6 CTAs, 4.6 waves: a 40 %-empty last wave) 2.7 % slower
 #endif
 
 __host__ __device__ inline size_t ro2_align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -75,10 +75,11 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     // TABLE: results in a dense [row][partner] table and a list with room for every pair of the
     // chunk (small N); otherwise row-contiguous segments and a list of bounded capacity, with the
     // exact group-wise evaluation for frames that overflow it
-    // (table row stride RS: an odd number of entries, so that the lanes of a quarter / half warp --
-    // one row each, the same partner column -- fall into different banks)
-    static constexpr int RS = N | 1;
-    static constexpr bool TABLE = (size_t)RW * RS * sizeof(V2) <= 5632;
+    // (table row: one column per partner -- partner j of agent i in column j - (j > i) -- at a stride
+    // RS of an odd number of entries, so that the lanes of a quarter / half warp -- one row each, the
+    // same column -- fall into different banks)
+    static constexpr int RS = (N - 1) | 1;
+    static constexpr bool TABLE = (size_t)RW * RS * sizeof(V2) <= 5120;
     static constexpr int LW = TABLE ? RW * RS : ((RW * (N - 1) < 128) ? RW * (N - 1) : 128);        // result slots
     static constexpr int LU = TABLE ? RW * (N - 1) / 2 : ((RW * (N - 1) / 2 < 64) ? RW * (N - 1) / 2 : 64);   // list entries
     static constexpr int GR = LW / (N - 1);                                       // rows per group (overflowing frames)
@@ -91,7 +92,8 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     V2 res[LW + 1];           // (d, log term) per ordered near pair, row-contiguous, ascending j; [LW]: (d_safety, 0)
     float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
     uint2 rowinfo[TABLE ? 1 : 32];   // (near mask, first result slot) of each row (segment layout only)
-    unsigned ent[LU + 1];     // unordered near pairs; [LU]: where lanes that ran out of pairs store
+    using Ent = typename std::conditional<TABLE, unsigned short, unsigned>::type;
+    Ent ent[LU + 1];          // unordered near pairs; [LU]: where lanes that ran out of pairs store
     unsigned umask[32];       // near AND not clipped (pair lanes clear the rare clipped-near bits)
     int cnt[TCW + 1];         // collision count per frame (slice); [TCW]: the call's record mask
     unsigned long long mbar[kRo2Stages];
@@ -237,6 +239,8 @@ __device__ __forceinline__ void ro2_fold_step(Real dx, Real dy, int j, Real delt
 }
 // `neutral` holds (d_safety, +0) for the whole call: never a candidate, adds nothing -- what a lane
 // that has run out of partners folds (one address for all of them: a broadcast, no bank conflict).
+// The fold runs over the row's COLUMNS (ascending column = ascending partner index) and leaves
+// column numbers in nj; the caller turns them into partner indices.
 template <typename Real, int K>
 __device__ __forceinline__ void ro2_fold_table(const typename vec2_of<Real>::type *__restrict__ rp,
                                                const typename vec2_of<Real>::type *__restrict__ neutral, unsigned mm, int i,
@@ -303,8 +307,13 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // (opaque to the optimiser: otherwise every use of a per-warp address re-derives them from %tid)
     asm volatile("" : "+r"(lane), "+r"(warp));
+    // One environment per CTA, one time segment per warp.  (Measured alternative: CTAs of four warps
+    // holding 4 / S environments of S segments each, so that 4096 environments run as ONE round of
+    // resident warps without any prefix pass: the environment index then lives in vector registers
+    // instead of uniform ones and the address arithmetic of every chunk grows -- 4 % slower at equal S,
+    // and S = 1, 2 lose to S = 4 even so.)
     const int S = blockDim.x >> 5;
-    const int e = blockIdx.x;                                    // one environment per CTA, one time segment per warp
+    const int e = blockIdx.x;
 
     // ---- per-CTA constants: end points, log table
     CS &C = *reinterpret_cast<CS *>(smem_raw);
@@ -538,7 +547,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             const int totU = (int)__reduce_add_sync(0xffffffffu, (unsigned)cUl);
             {
                 W.umask[lane] = m;
-                unsigned *ep = W.ent + baseU;
+                typename WS::Ent *ep = W.ent + baseU;
                 unsigned mm = mU;
                 const unsigned ew = (unsigned)lane | ((unsigned)i << 5);
                 const int iters = __reduce_max_sync(0xffffffffu, cUl);
@@ -546,7 +555,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 for (int it = 0; it < iters; ++it) {             // straight-line body: lanes out of pairs store to the spare slot
                     const bool on = mm != 0;
                     const unsigned j = (unsigned)(__ffs((int)mm) - 1);
-                    *(on ? ep : W.ent + WS::LU) = ew | (j << 10);
+                    *(on ? ep : W.ent + WS::LU) = (typename WS::Ent)(ew | (j << 10));
                     ep += on ? 1 : 0;
                     mm &= mm - 1;
                 }
@@ -558,7 +567,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 const int q = q0 + lane;
                 const bool valid = q < totU;
                 const unsigned w = W.ent[valid ? q : 0];
-                const int ri = (int)(w & 31u), ii = (int)((w >> 5) & 31u), j = (int)(w >> 10);
+                const int ri = (int)(w & 31u), ii = (int)((w >> 5) & 31u), j = (int)(w >> 10);                // j > ii
                 const int rj = ri - ii + j;
                 const V2 pi = W.pos[ri], pj = W.pos[rj];
                 V2 dv;
@@ -566,7 +575,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 ro2_eval_pair<Real>(dv.x, dv.y, coll, pi.x, pi.y, pj.x, pj.y, ds, rad, (Real)A.log_ds, (Real)A.inv_ds,
                                     a.log_mode, (Real)a.zero_eps, (Real)a.sentinel, logtab);
                 if (valid) {
-                    W.res[ri * WS::RS + j] = dv;
+                    W.res[ri * WS::RS + j - 1] = dv;              // columns: partner j > ii of row ri, partner ii < j of row rj
                     W.res[rj * WS::RS + ii] = dv;
                     if (coll) atomicAdd(&W.cnt[(ri - ii) / N], 2);                // both ordered pairs collide (:284,327)
                     if (!(dv.x != ds)) {                                          // near but clipped (inside the f32 margin)
@@ -576,7 +585,11 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 }
             }
             __syncwarp();
-            ro2_fold_table<Real, K>(W.res + lane * WS::RS, W.res + WS::LW, m, i, delta_eff, sum_all, sum_loc, nd, nj);
+            const unsigned lowi = (1u << i) - 1u;
+            const unsigned mcol = (m & lowi) | ((m >> 1) & ~lowi);               // near COLUMNS of the row
+            ro2_fold_table<Real, K>(W.res + lane * WS::RS, W.res + WS::LW, mcol, i, delta_eff, sum_all, sum_loc, nd, nj);
+#pragma unroll
+            for (int q = 0; q < K; ++q) nj[q] += (nj[q] >= i) ? 1 : 0;           // column -> partner index (-1 stays)
         } else {
         const int cFl = __popc(m), cUl = __popc(mU);
         int incl = cUl | (cFl << 16);                            // both counts in one scan
@@ -593,7 +606,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             {
                 W.rowinfo[lane] = make_uint2(m, (unsigned)baseF);
                 W.umask[lane] = m;
-                unsigned *ep = W.ent + ((incl & 0xffff) - cUl);
+                typename WS::Ent *ep = W.ent + ((incl & 0xffff) - cUl);
                 unsigned mm = mU;
                 // slot of (i, j) in row i's segment: its rank among the row's near partners
                 unsigned ew = (unsigned)lane | ((unsigned)i << 5) |

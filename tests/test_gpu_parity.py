@@ -356,11 +356,13 @@ def test_float32_free_running_episode_drift(n, grid, delta, box):
         assert nc64[live].sum() > 0
 
 
-@pytest.mark.parametrize("n,grid,delta,box", [(4, [5, 5], 1.0, None), (5, [5, 5], 1.0, 1.2), (8, [5, 5], 0.8, None),
-                                              (10, [5, 5], 1.0, 1.5), (16, [12, 12], 1.5, None), (20, [12, 12], 1.0, 4.0),
-                                              (32, [32, 32], 2.5, None), (32, [32, 32], 2.5, 6.0), (10, [5, 5], None, None)])
-def test_rollout2_every_instantiation_equals_general_kernel(n, grid, delta, box, monkeypatch):
-    """Every agent count the warp-per-segment kernel is instantiated for, sparse and dense (the dense
+@pytest.mark.parametrize("n,grid,delta,box,segs", [(4, [5, 5], 1.0, None, 0), (5, [5, 5], 1.0, 1.2, 0), (8, [5, 5], 0.8, None, 2),
+                                                   (10, [5, 5], 1.0, 1.5, 0), (16, [12, 12], 1.5, None, 4), (20, [12, 12], 1.0, 4.0, 1),
+                                                   (32, [32, 32], 2.5, None, 0), (32, [32, 32], 2.5, 6.0, 2), (10, [5, 5], None, None, 0),
+                                                   (10, [5, 5], 1.0, None, 1), (10, [5, 5], 1.0, 1.5, 2), (10, [5, 5], 1.0, None, 4),
+                                                   (10, [5, 5], 1.0, None, 8), (5, [5, 5], 1.0, None, 1)])
+def test_rollout2_every_instantiation_equals_general_kernel(n, grid, delta, box, segs, monkeypatch):
+    """Every agent count the warp-per-segment kernel is instantiated for, every segment count, sparse and dense (the dense
     cases overflow the pair list of the segment layout / fill the pair table), delta=None (every agent
     inside every Delta disk), T not a multiple of the chunk, environments that start late in their
     episode and finish inside the call, a second call continuing the first: bit-identical to the
@@ -369,7 +371,10 @@ def test_rollout2_every_instantiation_equals_general_kernel(n, grid, delta, box,
     E, T = 67, 53
     rng = np.random.default_rng(n)
     deltas = None if delta is None else np.ones(n) * delta
+    if segs:                                                       # time segments per environment (0: the plan's choice);
+        monkeypatch.setenv("DS_RO2_SEGS", str(segs))               # 1, 2: several environments per CTA, the last CTA not full
     new = BatchedDrones(E, n, grid, "O", 2, deltas, True, seed=3, warn=False)
+    monkeypatch.delenv("DS_RO2_SEGS", raising=False)
     monkeypatch.setenv("DS_RO2", "0")
     old = BatchedDrones(E, n, grid, "O", 2, deltas, True, seed=3, warn=False)
     monkeypatch.delenv("DS_RO2")
