@@ -341,7 +341,10 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
 
     // ---- the call's time axis is cut into S segments of whole chunks; warp k owns segment k
     const int nchunks = (T + TCW - 1) / TCW;
-    const int c0 = A.seg_c0[warp], c1 = A.seg_c0[warp + 1];      // this segment's chunks
+    int c0 = 0, c1 = 0;                                          // this segment's chunks
+#pragma unroll
+    for (int k = 0; k < kRo2MaxSeg; ++k)                         // (selects: a run-time index into the parameter block costs a local copy)
+        if (warp == k) { c0 = A.seg_c0[k]; c1 = A.seg_c0[k + 1]; }
     const int ta = c0 * TCW, Tend = (c1 * TCW < T) ? c1 * TCW : T;   // steps [ta, Tend) of the call
     const bool alive0 = ra.done[e] == 0;
     const int tenv0 = a.t[e];
@@ -396,11 +399,11 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             V2 *buf = &W.act[par2][0];
             if (rowlane) buf[lane] = u;
             __syncwarp();
+            const V2 *bufl = buf + (al ? lane : 0);              // (the other lanes run along on agent 0's actions; never looked at)
             unsigned hits = 0;
 #pragma unroll
             for (int q = 0; q < TCW; ++q) {
-                V2 uq{};
-                if (al) uq = buf[q * N + lane];
+                const V2 uq = bufl[q * N];
                 pend.x = add_rn(pend.x, mul_rn(dt, uq.x));
                 pend.y = add_rn(pend.y, mul_rn(dt, uq.y));
                 // every agent within goal_tol of its goal (:249-251): sqrt_rn(x) <= tol  <=>  x <= goal_t2
@@ -736,8 +739,8 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
             for (int kth = 1; kth <= K; ++kth) {
                 const int j = nj[kth - 1] < 0 ? 0 : nj[kth - 1];
                 const bool in_r = kth <= inr;                                     // :362-368
-                V2 pj = pm;
-                if (in_r && rowlane) pj = fpos[j];                                // (most rows of a sparse frame: ghosts, no load)
+                // (most rows of a sparse frame show ghosts: those lanes read one common address)
+                const V2 pj = *((in_r && rowlane) ? fpos + j : &W.pos[0]);
                 zrow[kth].x = in_r ? sub_rn(pj.x, pm.x) : ghx;
                 zrow[kth].y = in_r ? sub_rn(pj.y, pm.y) : ghy;
                 nirow[kth] = in_r ? j : -1;
