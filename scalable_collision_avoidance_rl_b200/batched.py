@@ -52,7 +52,11 @@ class BatchedDrones:
         self.log_mode = _lib.DS_LOG_DIV
         self.drone_radius = np.ones(self.n_agents) * formation.DRONE_RADIUS
         if constants is not None:
-            # (end_points, d_safety, deltas) given verbatim, e.g. by drones.rewards()
+            # (end_points, d_safety, deltas[, radii]) given verbatim, e.g. by drones.rewards()
+            if len(constants) > 3 and constants[3] is not None:
+                self.drone_radius = np.asarray(constants[3], np.float64).reshape(-1).copy()
+                if self.drone_radius.shape[0] != self.n_agents:
+                    raise ValueError("radii must have one entry per agent")
             self.end_points = np.asarray(constants[0], np.float64).reshape(-1, 1)
             self.d_safety = np.asarray(constants[1], np.float64).reshape(-1)
             self.deltas, clipped = np.asarray(constants[2], np.float64).reshape(-1), False

@@ -93,7 +93,7 @@ template <typename Real, int N> struct alignas(128) Ro2Warp {
     float4 posf[TCW * HP];    // packed f32 copies (x_2q, x_2q+1, y_2q, y_2q+1) per frame
     uint2 rowinfo[TABLE ? 1 : 32];   // (near mask, first result slot) of each row (segment layout only)
     using Ent = typename std::conditional<TABLE, unsigned short, unsigned>::type;
-    Ent ent[LU + 1];          // unordered near pairs; [LU]: where lanes that ran out of pairs store
+    Ent ent[LU + 32];         // unordered near pairs; [LU + lane]: where a lane that ran out of pairs stores
     unsigned umask[32];       // near AND not clipped (pair lanes clear the rare clipped-near bits)
     int cnt[TCW + 1];         // collision count per frame (slice); [TCW]: the call's record mask
     unsigned long long mbar[kRo2Stages];
@@ -555,10 +555,10 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
                 const unsigned ew = (unsigned)lane | ((unsigned)i << 5);
                 const int iters = __reduce_max_sync(0xffffffffu, cUl);
 #pragma unroll 1
-                for (int it = 0; it < iters; ++it) {             // straight-line body: lanes out of pairs store to the spare slot
+                for (int it = 0; it < iters; ++it) {             // straight-line body: lanes out of pairs store to their spare slot
                     const bool on = mm != 0;
                     const unsigned j = (unsigned)(__ffs((int)mm) - 1);
-                    *(on ? ep : W.ent + WS::LU) = (typename WS::Ent)(ew | (j << 10));
+                    *(on ? ep : W.ent + WS::LU + lane) = (typename WS::Ent)(ew | (j << 10));
                     ep += on ? 1 : 0;
                     mm &= mm - 1;
                 }

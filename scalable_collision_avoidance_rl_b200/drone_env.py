@@ -109,17 +109,18 @@ class drones:
         return state, z_states
 
     # ------------------------------------------------------------------ device engine
-    def _engine(self, end_points, d_safety, deltas) -> BatchedDrones:
+    def _engine(self, end_points, d_safety, deltas, radii=None) -> BatchedDrones:
         end_points = np.asarray(end_points, np.float64)
         d_safety = np.asarray(d_safety, np.float64)
         deltas = np.asarray(deltas, np.float64)
+        radii = None if radii is None else np.ascontiguousarray(radii, np.float64)
         key = (end_points.tobytes(), d_safety.tobytes(), deltas.tobytes(), self.k_closest,
-               bool(self.simplify_zstate), d_safety.shape[0])
+               bool(self.simplify_zstate), d_safety.shape[0], None if radii is None else radii.tobytes())
         eng = self._engines.get(key)
         if eng is None:
             n = d_safety.shape[0]
             eng = BatchedDrones(1, n, self.grid, "O", self.k_closest, None, self.simplify_zstate,
-                                constants=(end_points, d_safety, deltas),
+                                constants=(end_points, d_safety, deltas, radii),
                                 start_positions=np.zeros((1, n, 2)), warn=False)
             if len(self._engines) > 8:
                 self._engines.clear()
@@ -255,10 +256,10 @@ class drones:
 def _device_control(controller, state, env, u_max):
     """Both baseline controllers run on the device (ds_control) for the one environment of `env`."""
     state = np.asarray(state, np.float64)
-    if not np.array_equal(state[:, 4], env.drone_radius):
-        raise ValueError("the controllers take the agent radii from state[:, 4] (drone_env.py:632,643); "
-                         "this build holds them as the constants env.drone_radius and the two differ")
-    eng = env._engine(env.end_points, env.d_safety, env.deltas)
+    # the controllers take the agent radii from state[:, 4] (drone_env.py:632,643,664), not from
+    # env.drone_radius: a state whose radius column was edited gets an engine built on those radii
+    radii = None if np.array_equal(state[:, 4], env.drone_radius) else state[:, 4]
+    eng = env._engine(env.end_points, env.d_safety, env.deltas, radii)
     env._synced = None                                   # the device state is overwritten below
     eng.set_state(np.asarray(state, np.float64)[None], internal_t=env.internal_t)
     act = eng.control(controller, float(u_max))[0].cpu().numpy()

@@ -808,6 +808,29 @@ def test_dropin_controller_functions_vs_reference_golden(name, key, fn):
         assert np.array_equal(np.array(act), g[key][f], equal_nan=True), f"frame {f}"
 
 
+def test_dropin_controllers_take_the_radii_from_the_state():
+    """The reference's controllers read every agent's radius from state[:, 4] (drone_env.py:632,643,664),
+    not from env.drone_radius: a state with an edited radius column is served with those radii
+    (oracle with the same radii: bit-exact; and different from the answer for the default radii)."""
+    import drone_env
+    n = 6
+    rng = np.random.default_rng(5)
+    env = drone_env.drones(n, 0, [5, 5], "O", 2, np.ones(n), True)
+    state = env.state.copy()
+    state[:, 0:2] = rng.uniform(1.0, 2.2, (n, 2))
+    radii = rng.uniform(0.05, 0.25, n)
+    state[:, 4] = radii
+    for mode, um in ((c_oracle.CTRL_GRADIENT, 0.7), (c_oracle.CTRL_PROPORTIONAL, 1.0)):
+        want = c_oracle.control(mode, state[None, :, 0:2], env.end_points, env.d_safety, radii, um)[0]
+        base = c_oracle.control(mode, state[None, :, 0:2], env.end_points, env.d_safety, None, um)[0]
+        if mode == c_oracle.CTRL_GRADIENT:
+            got = np.array(drone_env.gradient_control(state, env, u_max=um))
+            assert not np.array_equal(want, base)                  # the radii matter for the barrier gradient
+        else:
+            got = np.array(drone_env.proportional_control(state, env))
+        assert np.array_equal(got, want, equal_nan=True), mode
+
+
 def test_controllers_vs_oracle_dense_batch():
     """Both controllers on dense random batches (many pairs inside d_safety) against the oracle,
     through the closed-loop step: the action taken is left in vel."""

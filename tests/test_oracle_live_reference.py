@@ -154,6 +154,9 @@ def test_controllers_against_the_live_reference(rowlib, n, grid, box, u_max):
     rad = np.ascontiguousarray(env.drone_radius)
     for f in range(20):
         env.state[:, 0:2] = rng.uniform(0, box, (n, 2))
+        if f >= 12:                                                              # the controllers read the radii from the state
+            env.state[:, 4] = rng.uniform(0.05, 0.25, n)
+            rad = np.ascontiguousarray(env.state[:, 4])
         if f == 3:
             env.state[1, 0:2] = env.state[0, 0:2] + [rad[0] + rad[1], 0.0]      # exact contact: division by zero
         if f == 4:
@@ -167,5 +170,5 @@ def test_controllers_against_the_live_reference(rowlib, n, grid, box, u_max):
             rowlib.rowcheck_control(mode, n, *[x.ctypes.data_as(ctypes.c_void_p) for x in (pos, xF, dsf, rad)],
                                     ctypes.c_double(um), act.ctypes.data_as(ctypes.c_void_p))
             assert np.array_equal(act, want[mode], equal_nan=True), (f, mode)
-            got = c_oracle.control(mode, pos[None], env.end_points, env.d_safety, None, um)[0]
+            got = c_oracle.control(mode, pos[None], env.end_points, env.d_safety, rad, um)[0]
             assert np.array_equal(got, want[mode], equal_nan=True), (f, mode, "oracle")
