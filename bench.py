@@ -456,7 +456,7 @@ class GpuLeg:
         self.torch.cuda.empty_cache()
 
 
-def roofline_of(kms, bpas, units_per_launch, workload, dtype_name):
+def roofline_of(kms, bpas, units_per_launch, workload, dtype_name, kernel):
     hbm_peak, peak_src = peaks()
     alg = bpas * units_per_launch
     avg_ms, med_ms = float(np.mean(kms)), float(np.median(kms))
@@ -465,7 +465,7 @@ def roofline_of(kms, bpas, units_per_launch, workload, dtype_name):
     return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu --set full)",
             "traffic_source": None if ent is None else {k: ent.get(k) for k in ("capture", "kernel_commit")},
-            "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "kernel": "ds::rollout_kernel",
+            "algorithmic_bytes_per_launch": alg, "peak_source": peak_src, "kernel": kernel,
             "bytes_per_agent_step": bpas, "avg_launch_ms": avg_ms, "median_launch_ms": med_ms,
             "min_launch_ms": float(np.min(kms)), "launches_timed": len(kms),
             "note": "timed with CUDA events around every rollout launch of the timed region, on the launch stream"}
@@ -496,7 +496,7 @@ def run_ours(args, wl):
     launches = leg.launches
     value = world * E * n * T * K / (ms * 1e-3)
     bpas = bytes_per_agent_step(rb, n)
-    roof = roofline_of(kms, bpas, E * n * T, args.workload, args.dtype)
+    roof = roofline_of(kms, bpas, E * n * T, args.workload, args.dtype, leg.env.rollout_kernel)
     agg_check = leg.agg_check()
 
     # end to end through the public host API: pinned host action stream in, pinned host
@@ -572,7 +572,7 @@ def run_ours(args, wl):
                   "value": w2["E"] * w2["n"] * EPISODE * K2 / (ms2 * 1e-3), "unit": "agent-steps/s",
                   "ms_per_step": ms2 / K2,
                   "roofline": roofline_of(kms2, bytes_per_agent_step(rb, w2["n"]), (hi - lo) * w2["n"] * EPISODE, name,
-                                          args.dtype),
+                                          args.dtype, l2.env.rollout_kernel),
                   "agg_check": chk}
             if name == "config5":
                 ex["note"] = (f"{hi - lo} environments = {hi - lo} CTAs per GPU" +

@@ -135,6 +135,11 @@ int ds_device_count(void);
 /* drones.__init__ / init_agents constants -> device (drone_env.py:55-96). */
 int ds_create(const ds_config *cfg, ds_handle **out);
 void ds_destroy(ds_handle *h);
+/* Name of the kernel ds_rollout / ds_rollout_host launch for this handle: "ds::rollout2_kernel" (one warp
+ * per environment and time segment: uniform d_safety / Delta / radius, k = 2, 2-column observation,
+ * n in {4, 5, 8, 10, 16, 20, 32}) or "ds::rollout_kernel" (every other configuration).  For benchmark
+ * and profile records; the choice is made once, in ds_create. */
+const char *ds_rollout_kernel_name(const ds_handle *h);
 /* Fill *p with the reference's module constants (drone_env.py:29-30,72,...). */
 void ds_default_params(ds_params *p);
 

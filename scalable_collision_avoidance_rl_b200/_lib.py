@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "ds_set_state", "ds_get_state", "ds_reset", "ds_step_host", "ds_step_host_block", "ds_rollout_host", "ds_returns",
     "ds_step_control", "ds_rollout_control", "ds_reset_random",
     "ds_policy_create", "ds_policy_destroy", "ds_policy_forward", "ds_rollout_policy", "ds_control",
+    "ds_rollout_kernel_name",
 )
 
 
@@ -115,12 +116,14 @@ def load():
             "(nvcc, sm_100a). This package has no CPU implementation of drone_env.step().")
     lib = ctypes.CDLL(path)
     lib.ds_last_error.restype = ctypes.c_char_p
+    lib.ds_rollout_kernel_name.restype = ctypes.c_char_p
+    lib.ds_rollout_kernel_name.argtypes = [ctypes.c_void_p]
     lib.ds_destroy.restype = None
     lib.ds_default_params.restype = None
     lib.ds_policy_destroy.restype = None
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)   # AttributeError if the ABI is incomplete
-        if name not in ("ds_last_error", "ds_destroy", "ds_default_params", "ds_policy_destroy"):
+        if name not in ("ds_last_error", "ds_destroy", "ds_default_params", "ds_policy_destroy", "ds_rollout_kernel_name"):
             fn.restype = ctypes.c_int
     _lib = lib
     return lib

@@ -125,6 +125,11 @@ class BatchedDrones:
         self.reset(start_positions)
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def rollout_kernel(self) -> str:
+        """The kernel rollout() launches for this configuration (ds_rollout_kernel_name)."""
+        return self.lib.ds_rollout_kernel_name(self._h).decode()
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

@@ -617,6 +617,11 @@ try {
     return fail(DS_ERR_INTERNAL, "ds_create: unknown host exception");
 }
 
+const char *ds_rollout_kernel_name(const ds_handle *h)
+{
+    return (h && h->ro2_ok) ? "ds::rollout2_kernel" : "ds::rollout_kernel";
+}
+
 void ds_destroy(ds_handle *h)
 {
     if (!h) return;
