@@ -1054,7 +1054,7 @@ template <typename Real> struct RoSmem {
     __host__ __device__ static size_t bytes(int n, int G, int TC, int L)
     {
         const size_t A = (size_t)G * n, I = A * TC, F = (size_t)G * TC;
-        return (3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2) + kLogTabSize * sizeof(LogTabEntry) +
+        return align16((3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2)) + kLogTabSize * sizeof(LogTabEntry) +
                align16(n * sizeof(Real)) + align16(n * sizeof(int)) + align16(n * sizeof(float)) +
                2 * F * ((n + 1) / 2) * sizeof(float4) + align16(I * sizeof(int)) +
                align16((size_t)L * sizeof(unsigned)) + align16(F * sizeof(int)) +
@@ -1068,8 +1068,8 @@ template <typename Real> struct RoSmem {
         cA = reinterpret_cast<V2 *>(p); cB = cA + n; cF = cB + n;
         act_ = cF + n; pos_ = act_ + 3 * I;
         p0 = pos_ + 2 * I; vfin = p0 + A; accv = vfin + A; res = accv + I;
-        p += (3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2);
-        logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);
+        p += align16((3 * (size_t)n + 6 * I + 2 * A + (size_t)L) * sizeof(V2));   // (float32: an odd count of float2 would
+        logtab = reinterpret_cast<LogTabEntry *>(p); p += kLogTabSize * sizeof(LogTabEntry);   // leave the float4 frames misaligned)
         hp_ = (n + 1) / 2; F_ = (int)F;
         pf_ = reinterpret_cast<float4 *>(p); p += 2 * F * hp_ * sizeof(float4);
         cT = reinterpret_cast<Real *>(p); p += align16(n * sizeof(Real));
