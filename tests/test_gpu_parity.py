@@ -450,6 +450,53 @@ def test_log_mode_rcp_within_stated_difference():
     assert (a["true_reward"] - b["true_reward"]).abs().max().item() <= 1e-13
 
 
+@pytest.mark.parametrize("n,k,simplify", [(3, 2, True), (5, 2, True), (5, 3, False), (7, 1, True), (9, 2, False),
+                                          (11, 3, True), (33, 2, True), (33, 2, False), (129, 2, True)])
+def test_float32_mode_every_kernel_on_odd_shapes(n, k, simplify):
+    """float32 instantiations of every kernel on agent counts / neighbour counts / layouts that make the
+    shared-memory pieces odd-sized (an 8-byte float2 block in front of 16-byte data was a real bug at
+    n = 5): observe, step, both rollout forms, both controllers (one step and fused), device reset --
+    all must run (a misaligned access poisons the context) and track the float64 twin on the same
+    inputs to float32 accuracy."""
+    from scalable_collision_avoidance_rl_b200 import BatchedDrones, formation
+    E, T = 37, 11
+    grid = [5, 5] if n <= 11 else [32, 32] if n <= 33 else [64, 64]
+    rng = np.random.default_rng(n * 10 + k)
+    envs = [BatchedDrones(E, n, grid, "O", k, np.ones(n), simplify, dtype=dt, seed=4, warn=False)
+            for dt in (torch.float32, torch.float64)]
+    tab = formation.unit_action_table(16)
+    idx = torch.as_tensor(rng.integers(0, 16, (T, E, n)).astype(np.uint8), device=envs[0].device)
+    res = []
+    for env in envs:
+        env.reset_random(seed=9, stream=1)
+        env.observe()
+        z0 = env.z_states.double().clone()
+        (pos1, _), z1, r1, nc1, *_ = env.step(torch.as_tensor(tab[idx[0].cpu().numpy()], device=env.device).to(env.dtype))
+        pos1, r1 = pos1.double().clone(), r1.double().clone()
+        a = env.rollout(action_idx=idx, action_table=tab, record=("pos", "reward", "true_reward", "obs", "ncoll", "finished"))
+        b = env.rollout(actions=torch.as_tensor(tab[idx.cpu().numpy()], device=env.device).to(env.dtype), record=("pos", "reward"))
+        env.reset_random(seed=9, stream=2)
+        (pc, vc), *_ = env.step_control("gradient", u_max=0.9)
+        pc = pc.double().clone()
+        c = env.rollout_control(5, "proportional", record=("pos", "reward"))
+        torch.cuda.synchronize()
+        res.append((z0, pos1, r1, a["pos"].double(), a["reward"].double(), a["ncoll"], a["finished"], b["pos"].double(),
+                    pc, c["pos"].double()))
+    f32, f64 = res
+    g = float(max(grid))
+    # (the observations themselves are not compared: on lattice starts the k nearest are exact ties that
+    # float32 rounding breaks differently; positions and rewards do not depend on the choice)
+    assert torch.isfinite(f32[0]).all()
+    for name, x, y, tol in (("pos after one step", f32[1], f64[1], 1e-6 * g),
+                            ("rollout pos", f32[3], f64[3], 2e-5 * g), ("second rollout pos", f32[7], f64[7], 4e-5 * g),
+                            ("controller step", f32[8], f64[8], 1e-5 * g), ("controller rollout", f32[9], f64[9], 4e-5 * g)):
+        assert torch.isfinite(x).all(), name
+        assert (x - y).abs().max().item() <= tol, (name, (x - y).abs().max().item())
+    assert torch.equal(f32[6], f64[6])                             # nobody finishes in 11 steps: same flags
+    rel = ((f32[4] - f64[4]).abs() / f64[4].abs().clamp_min(1.0))
+    assert rel.median().item() <= 1e-5
+
+
 def test_float32_handle_side_paths():
     """The float32 instantiations of everything around the step (device reset, actors, closed loops,
     returns): consistent with each other bit for bit, and with the fp64 restatements to fp32
