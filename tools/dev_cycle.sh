@@ -2,7 +2,7 @@
 # dev loop (build container): rebuild libdronestep.so, keep a copy of it next to the results (so that
 # ncu reports can be joined with the right SASS later), then run a GPU script through gpurun.
 # usage: tools/dev_cycle.sh TAG "gpu command using \$TAG" [gpurun timeout]
-set -e
+set -e -o pipefail
 cd /root/repo
 TAG=$1; CMD=$2; TMO=${3:-1500}
 python -c "import __graft_entry__ as g; g.build()" | tail -1
