@@ -1,4 +1,5 @@
-// dronestep_rollout2.cuh -- warp-per-environment rollout kernel (the benchmarked kernel of round 2).
+// dronestep_rollout2.cuh -- warp-per-(environment, time segment) rollout kernel (the benchmarked
+// kernel of round 2; DESIGN.md section 4.3 has the measurements behind every choice below).
 //
 // Same observable behaviour as rollout_kernel (dronestep_kernels.cuh): T fused steps of
 // drones.step() (reference drone_env.py:214-258) per environment, every per-step output recorded,
@@ -7,29 +8,34 @@
 // issue (58 % issue slots, 1.07 barrier-stall cycles per issue, 1410 warp-instructions per 32
 // agent-steps of which only ~12 % were fp64 arithmetic):
 //
-//   * ONE WARP owns ONE environment for the whole call and walks its episode in chunks of
-//     TCW = floor(32 / N) consecutive time slices: lane = (slice s, agent i), one row of the pair
-//     matrix per lane.  Nothing is shared between warps but the per-CTA constants, so the chunk
-//     loop has NO CTA barrier -- only __syncwarp between its phases.
+//   * One CTA per environment, ONE WARP per TIME SEGMENT of the call: the warp first integrates the
+//     steps in front of its segment (the prefix pass: integrator + episode-end test only), then
+//     walks the segment in chunks of TCW = floor(32 / N) consecutive time slices: lane = (slice s,
+//     agent i), one row of the pair matrix per lane.  Nothing is shared between warps but the
+//     per-CTA constants, so the chunk loop has NO CTA barrier -- only __syncwarp between its phases.
 //   * N (agents) is a template parameter: slice / agent of a lane, trip counts, shared-memory
 //     offsets are compile-time; the phases are written as straight-line predicated code with
 //     warp-uniform loop bounds (no divergent branches in the chunk loop's hot phases).
-//   * The episode's action stream is moved by the TMA unit: per chunk one cp.async.bulk
-//     (global -> shared, mbarrier complete_tx) per time slice brings that slice's contiguous
-//     [N][2] block into a 3-deep ring, two chunks ahead of its use; no thread holds an action in
-//     a register while it waits.  A lane-load form remains for index mode / unaligned blocks.
+//   * The episode's action stream is moved by the TMA unit: per chunk ONE cp.async.bulk.tensor.2d
+//     (tensor map over [T][E * N * 2], box {N * 2, TCW}; mbarrier complete_tx) brings the chunk's
+//     [TCW][N][2] block into a 2-stage ring, one chunk ahead of its use; no thread holds an action
+//     in a register while it waits.  Fallbacks: one 1-D cp.async.bulk per slice; a lane-load form
+//     for index mode / unaligned blocks.
 //   * Every agent has the same radius, d_safety and Delta in every configuration the reference
 //     can construct with a scalar delta (drone_env.py:75,85-91,153 on a circle formation), and
 //     then d_ij, log(d_safety/d_ij), the collision test and the Delta-disk test are symmetric in
 //     (i, j): each UNORDERED near pair is evaluated once (one sqrt / log instead of two) and its
-//     result is scattered to the result segments of both rows.  Non-uniform constants, other n,
-//     k != 2 and the 5-column observation take rollout_kernel (the host decides per handle).
-//   * A row folds its segment in ascending j (sums; k nearest with strict "<" insertion = stable
+//     result is scattered to both rows of a dense [row][partner column] table (small N) or to the
+//     rows' result segments.  Non-uniform constants, other n, k != 2 and the 5-column observation
+//     take rollout_kernel (the host decides per handle; ds_rollout_kernel_name tells which).
+//   * A row folds its partners in ascending j (sums; k nearest with strict "<" insertion = stable
 //     argsort order); collision counts are posted by the pair lanes (rare), the Delta-disk count
 //     follows from the k nearest (uniform Delta), so the fold loop carries only what needs order.
 //   * Frames too dense for the list (more near pairs than its capacity) are evaluated in groups
 //     of rows, every pair of a group's rows exactly, through the same fold -- correct for any
 //     density, never taken at the BASELINE densities.
+//   * 72 registers (everything a lane carries across chunks lives in the warp's shared-memory
+//     block) and <= 32 KB of shared memory per 4-warp CTA: 7 CTAs per SM.
 //
 // The arithmetic (operation order of eval_pair / row_end / write_obs) is that of
 // dronestep_kernels.cuh, so this kernel, rollout_kernel and step_kernel agree bit for bit.
@@ -462,7 +468,7 @@ rollout2_kernel(const Ro2Args A, const __grid_constant__ CUtensorMap tmap)
         W.cnt[TCW] = (int)((ra.pos_tr ? 1u : 0u) | (ra.vel_tr ? 2u : 0u) | (ra.r_tr ? 4u : 0u) | (ra.tr_tr ? 8u : 0u) |
                           (ra.z_tr ? 16u : 0u) | (ra.ncoll_tr ? 32u : 0u) | (ra.fin_tr ? 64u : 0u));   // record mask
 
-    // ---- action staging.  TMA: lane 0 brings chunk c's [TCW][N][2] block into ring stage (c - c0) % 3
+    // ---- action staging.  TMA: lane 0 brings chunk c's [TCW][N][2] block into ring stage (c - c0) % 2
     // (one 2-D tile, or one 1-D bulk copy per slice); lane-load form: every row lane holds the action
     // of its row one chunk ahead.
     const unsigned act_s32 = ro2_smem_u32(&W.act[0][0]), mbar_s32 = ro2_smem_u32(&W.mbar[0]);
